@@ -1,0 +1,171 @@
+/*
+ * rtgrff.h — C ABI of librtgrff_b200.so: the B200 (sm_100a) implementation of the per-ray hot
+ * path of peijin94/raytracingGRFF (ray integrator -> LOS resampler -> GRFF transfer).
+ *
+ * Plain C types, raw pointers and sizes only.  Every entry point cites the reference interface
+ * it replaces (paths are inside the reference repository).  All functions return 0 on success
+ * and a negative RTGRFF_E* code on failure (PyGET_MW keeps GRFF's convention: 0 ok, >0 error);
+ * rtgrff_last_error() returns a thread-local message for the last failure.
+ *
+ * Buffers marked "host" are caller-owned host memory (pageable or pinned); device memory is
+ * owned by the library behind the opaque context, one context per GPU.  A context is not
+ * thread-safe; use one per thread (the reference's path is single-threaded as well).
+ */
+#ifndef RTGRFF_H
+#define RTGRFF_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTGRFF_OK 0
+#define RTGRFF_EINVAL (-1)      /* bad argument / size                                   */
+#define RTGRFF_ECUDA (-2)       /* CUDA runtime error (message has the cudaError string)  */
+#define RTGRFF_ENOCUBE (-3)     /* the cube this call needs has not been uploaded        */
+#define RTGRFF_ENOMEM (-4)
+#define RTGRFF_EUNSUPPORTED (-5)
+
+typedef struct rtgrff_ctx rtgrff_ctx;
+
+/* Library / build identification ("rtgrff_b200 <version> sm_100a"). */
+const char *rtgrff_version(void);
+const char *rtgrff_last_error(void);
+/* Number of CUDA devices visible; <0 on error (no driver, no GPU). */
+int rtgrff_device_count(void);
+
+/* One context per GPU.  `stream` is a cudaStream_t passed as void* (NULL = the library creates
+ * its own non-blocking stream).  Passing torch's current stream makes torch CUDA events see the
+ * library's kernels. */
+int rtgrff_ctx_create(int device, void *stream, rtgrff_ctx **out);
+int rtgrff_ctx_destroy(rtgrff_ctx *ctx);
+int rtgrff_ctx_synchronize(rtgrff_ctx *ctx);
+/* Kernel launches issued by this context since creation (for bench.py's gpu_launches). */
+int64_t rtgrff_ctx_launch_count(const rtgrff_ctx *ctx);
+
+/*
+ * Grid geometry of one axis: {g[0], mean step, g[n-1], g[1]-g[0]}: (g0, step) exactly as the
+ * reference's _check_uniform_grid returns them (raytracingGRFF/gpu_raytrace.py:21-33), the last
+ * node, which scipy's bounds test uses (build_rays.py:140), and the spacing np.gradient is given
+ * (build_rays.py:132-138).  geom[12] = {x0,dx,xl,hx, y0,dy,yl,hy, z0,dz,zl,hz}.
+ */
+
+/*
+ * Upload omega_pe (nx,ny,nz) C-order float64 [rad/s] and build the interleaved
+ * {omega_pe, d/dx, d/dy, d/dz} float32 cube on the device with numpy.gradient semantics.
+ * Replaces: build_rays.py:132-143 (np.gradient x3 + four RegularGridInterpolator) and
+ * gpu_raytrace.py:354-357 (H2D + cp.gradient x3).  `omega_pe` is host memory unless
+ * `on_device` != 0 (then a device pointer readable from ctx's device).
+ */
+int rtgrff_set_omega_cube(rtgrff_ctx *ctx, const double *omega_pe, int nx, int ny, int nz,
+                          const double geom[12], int on_device);
+
+/*
+ * Upload the model fields sampled along the rays, each (nx,ny,nz) C-order float32 host arrays:
+ * n_e [cm^-3], T [K], |B| [G]; bx,by,bz [G] may be NULL (then theta = 90 deg everywhere, as the
+ * reference hard-codes at script/resample_with_ray_tracing.py:495).
+ * Replaces: gpu_raytrace.py:681 (per-call H2D of each field) / :647-649.
+ */
+int rtgrff_set_field_cubes(rtgrff_ctx *ctx, const float *ne, const float *te, const float *b,
+                           const float *bx, const float *by, const float *bz,
+                           int nx, int ny, int nz, const double geom[12]);
+
+/* How the cross-section ratio S is recorded. */
+#define RTGRFF_S_PER_STEP 0     /* CPU reference: ratio of the recorded step only (build_rays.py:239-244) */
+#define RTGRFF_S_CUMULATIVE 1   /* CUDA reference: running product since the start (gpu_raytrace.py:398-408) */
+
+/*
+ * Integrate n_rays rays for n_steps RK4 steps.  Replaces build_rays.ray_trace
+ * (build_rays.py:128-248) and gpu_raytrace._trace_ray_gpu (gpu_raytrace.py:328-411).
+ *  x_start,y_start,z_start: host float64 (n_rays); kvec: host float64 (n_rays,3) unit directions.
+ *  r_record: host float64 (n_rec,n_rays,3) or NULL; s_record: host float64 (n_rec,n_rays) or NULL
+ *  (ignored unless trace_cs); n_rec = ceil(n_steps/record_stride), record i taken after step
+ *  i*record_stride.  The records also stay on the device for rtgrff_sample_traced().
+ *  active_steps (optional, host): central-ray steps taken while the ray still moved.
+ */
+int rtgrff_trace(rtgrff_ctx *ctx, int64_t n_rays, const double *x_start, const double *y_start,
+                 const double *z_start, const double *kvec, double freq_hz, double dt,
+                 int64_t n_steps, int64_t record_stride, int trace_cs, double perturb_ratio,
+                 int s_mode, double *r_record, double *s_record, int64_t *active_steps);
+
+/*
+ * Sample n_e, T, |B| along recorded paths and compute validity and segment lengths.
+ * Replaces gpu_raytrace._sample_model_with_rays_cuda/_cpu (gpu_raytrace.py:632-709), including
+ * the per-ray Python loop _compute_ds_from_valid (:473-486).  float32 arithmetic as numpy does it.
+ *  pos: host float32 (n_rec,n_rays,3); s: host float32 (n_rec,n_rays); ray_start: host float32 (n_rays,3).
+ *  Outputs, host, (n_rec,n_rays): ne,te,b,ds float32; valid uint8 (0/1).
+ */
+int rtgrff_sample(rtgrff_ctx *ctx, int64_t n_rec, int64_t n_rays, const float *pos, const float *s,
+                  const float *ray_start, double r_sun_cm, double fill_ne, double fill_te,
+                  double fill_b, float *ne, float *te, float *b, float *ds, uint8_t *valid);
+
+/* Same, on the records left on the device by the last rtgrff_trace() (no host round trip of the
+ * paths).  Positions and S are rounded to float32 first, as the reference does (gpu_raytrace.py:642-643).
+ * Any output pointer may be NULL; results also stay on the device for rtgrff_emission_traced(). */
+int rtgrff_sample_traced(rtgrff_ctx *ctx, const float *ray_start, double r_sun_cm, double fill_ne,
+                         double fill_te, double fill_b, float *ne, float *te, float *b, float *ds,
+                         uint8_t *valid, float *s);
+
+/*
+ * GRFF single line of sight.  Same symbol, argument list and array layouts as
+ * GRFF_DEM_Transfer.so::PyGET_MW bound at script/resample_with_ray_tracing.py:79-86:
+ *  Lparms int32[5] {Nz,Nf,NT,DEMkey,DDMkey}; Rparms f64[3] {area cm^2, f0 Hz, log10 step};
+ *  Parms f64 (15,Nz) column-major; T_arr/DEM_arr/DDM_arr unused (NT must be 0);
+ *  RL f64 (7,Nf) column-major, written.  Returns 0 ok, 1 bad sizes, 2 DEM/DDM requested,
+ *  3 CUDA failure.  Runs on device 0 through a process-wide context.
+ */
+int PyGET_MW(const int32_t *Lparms, const double *Rparms, const double *Parms,
+             const double *T_arr, const double *DEM_arr, const double *DDM_arr, double *RL);
+
+/*
+ * GRFF batched over pixels, fastGRFF get_mw_slice layout (script/resample_with_ray_tracing.py:404-446):
+ *  Lparms_M int32[6] {Npix,Nz,Nf,NT,DEMkey,DDMkey}; Rparms_M f64 (3,Npix); Parms_M f64 (15,Nz,Npix);
+ *  RL_M f64 (7,Nf,Npix) written; status int32 (Npix) written; all host, Fortran order.
+ */
+int rtgrff_get_mw_slice(rtgrff_ctx *ctx, const int32_t *Lparms_M, const double *Rparms_M,
+                        const double *Parms_M, const double *T_arr, const double *DEM_arr,
+                        const double *DDM_arr, double *RL_M, int32_t *status);
+
+/*
+ * GRFF + T_b conversion on the samples left on the device by rtgrff_sample_traced(): the
+ * per-pixel loop of script/resample_with_ray_tracing.py:467-530 (valid filter, Parms packing with
+ * theta=90, flag 1+4, s_max 30; GET_MW; SFU -> T_b; V/I; nan_to_num) without materialising Parms.
+ *  tb, vi: host float64 (n_rays, n_freq) (= emission_cube / emission_polVI_cube flattened over pixels).
+ */
+int rtgrff_emission_traced(rtgrff_ctx *ctx, double pixel_area_cm2, double freq0_hz, int n_freq,
+                           double freq_log_step, int em_flag, int s_max, double *tb, double *vi);
+
+/* Per-frequency settings of the fused map renderer. */
+typedef struct {
+    double freq_hz;        /* ray frequency = emission frequency */
+    double dt;             /* integrator step [s] */
+    int64_t n_steps;
+    int64_t record_stride;
+} rtgrff_freq_params;
+
+#define RTGRFF_ORDER_RECORD 0    /* voxels handed to GRFF in record order (observer first), as the
+                                    reference does for ray-traced maps (script/...:481-501)          */
+#define RTGRFF_ORDER_REVERSED 1  /* far end first, observer last (GRFF's physical convention)          */
+
+/*
+ * Fused map: for every pixel and every frequency, trace the ray, sample the fields at each record
+ * and integrate the transfer equation, without materialising paths.  Equivalent to
+ * run_ray_tracing_emission (script/resample_with_ray_tracing.py:295-530) called once per frequency
+ * as the publication drivers do (script/pub/TbSpectra_gen.py:155-182).
+ *  Rays: x_start,y_start,z_start host float64 (n_rays), direction (0,0,-1) unless kvec != NULL.
+ *  use_bvec: 0 -> theta=90 deg (reference behaviour); 1 -> theta from B.t along the ray (needs bx,by,bz).
+ *  tb, vi: float64 (n_freq, n_rays); host, or device pointers when out_on_device != 0.
+ *  stats (optional, host int64[2]): {nominal ray-steps, active ray-steps}.
+ */
+int rtgrff_render_map(rtgrff_ctx *ctx, int64_t n_rays, const double *x_start, const double *y_start,
+                      const double *z_start, const double *kvec, int n_freq,
+                      const rtgrff_freq_params *freqs, int trace_cs, double perturb_ratio,
+                      double pixel_area_cm2, double r_sun_cm, int em_flag, int s_max, int use_bvec,
+                      int voxel_order, double *tb, double *vi, int out_on_device, int64_t *stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTGRFF_H */

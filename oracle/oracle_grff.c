@@ -33,6 +33,8 @@
  *   slab:      I <- I e^-tau + S (1-e^-tau), tau = kappa dz;
  *   cutoff:    a mode with n^2<=0 (or X above its cutoff v >= 1-sqrt u, or u>=1) is
  *              evanescent in that voxel: I_s <- 0, no emission;
+ *   empty voxel: dz<=0, T<=0, n_e<=0, B<0 or non-finite -> transparent; no layer is placed
+ *              between an empty voxel and its neighbours;
  *   gyroresonance layers (Parms[6] bit0 clear) between consecutive voxels where
  *              s nu_B crosses nu, s=2..s_max: B, n_e, T, theta linear between voxel
  *              centres, L_B = B_res dz_mid/|dB|,
@@ -213,8 +215,10 @@ int oracle_get_mw(const int32_t *Lparms, const double *Rparms, const double *Par
             vx.gr_on = !(flag & 1); vx.ff_on = !(flag & 2);
             vx.smax = (int)P[7];
             if (!(vx.dz > 0.0) || !(vx.T > 0.0) || !(vx.ne > 0.0) || !(vx.B >= 0.0) ||
-                !isfinite(vx.dz) || !isfinite(vx.T) || !isfinite(vx.ne) || !isfinite(vx.B) || !isfinite(vx.th))
-                continue;                                    /* empty / invalid voxel: transparent */
+                !isfinite(vx.dz) || !isfinite(vx.T) || !isfinite(vx.ne) || !isfinite(vx.B) || !isfinite(vx.th)) {
+                have_prev = 0;                               /* empty / invalid voxel: transparent, */
+                continue;                                    /* and no layer is placed across it    */
+            }
             vx.cth = cos(vx.th); vx.sth = sin(vx.th);
             if (have_prev && vx.B > 0.0 && prev.B > 0.0) between(I6, nu, &prev, &vx);
             const int x_to_R = vx.cth >= 0.0;

@@ -1,0 +1,13 @@
+"""raytracinggrff_b200 — B200 (sm_100a) implementation of the per-ray hot path of
+peijin94/raytracingGRFF behind the reference's own Python API.
+
+Exports mirror ``raytracingGRFF/__init__.py:3-15`` for the hot path (``C_R``, ``ray_trace``,
+``trace_ray``, ``sample_model_with_rays``); the MAS/psipy helpers and ``patch_nan_emission_map``
+are out of scope.  Nothing here imports ``oracle/``.
+"""
+from .build_rays import ray_trace
+from .gpu_raytrace import C_R, sample_model_with_rays, trace_ray
+from .grff import get_mw_slice, initGET_MW
+from .session import RaySession
+
+__all__ = ["C_R", "RaySession", "get_mw_slice", "initGET_MW", "ray_trace", "sample_model_with_rays", "trace_ray"]

@@ -1,0 +1,196 @@
+"""ctypes binding of librtgrff_b200.so (C ABI: include/rtgrff.h).
+
+There is no CPU fallback: if the shared library has not been built, or no CUDA device is
+visible, the first call raises.  Build with ``python -c "import __graft_entry__ as g; g.build()"``
+or ``python -m raytracinggrff_b200.build``.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint8, c_void_p
+from pathlib import Path
+
+import numpy as np
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "librtgrff_b200.so"
+
+RTGRFF_OK = 0
+RTGRFF_EINVAL = -1
+RTGRFF_ECUDA = -2
+RTGRFF_ENOCUBE = -3
+RTGRFF_ENOMEM = -4
+RTGRFF_EUNSUPPORTED = -5
+
+S_PER_STEP = 0
+S_CUMULATIVE = 1
+ORDER_RECORD = 0
+ORDER_REVERSED = 1
+
+# every symbol include/rtgrff.h declares (tests check the library exports all of them)
+EXPORTS = (
+    "rtgrff_version", "rtgrff_last_error", "rtgrff_device_count", "rtgrff_ctx_create", "rtgrff_ctx_destroy",
+    "rtgrff_ctx_synchronize", "rtgrff_ctx_launch_count", "rtgrff_set_omega_cube", "rtgrff_set_field_cubes",
+    "rtgrff_trace", "rtgrff_sample", "rtgrff_sample_traced", "PyGET_MW", "rtgrff_get_mw_slice",
+    "rtgrff_emission_traced", "rtgrff_render_map",
+)
+
+
+class FreqParams(ctypes.Structure):
+    """rtgrff_freq_params."""
+    _fields_ = [("freq_hz", c_double), ("dt", c_double), ("n_steps", c_int64), ("record_stride", c_int64)]
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and declare the prototypes.  Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: the CUDA extension has not been built and this package has no CPU "
+            "fallback. Run `python -m raytracinggrff_b200.build` (needs nvcc) first.")
+    lib = ctypes.CDLL(str(LIB_PATH))
+    dp, fp, ip = POINTER(c_double), POINTER(c_float), POINTER(c_int32)
+    lib.rtgrff_version.restype = c_char_p
+    lib.rtgrff_last_error.restype = c_char_p
+    lib.rtgrff_device_count.restype = c_int
+    lib.rtgrff_ctx_create.argtypes = [c_int, c_void_p, POINTER(c_void_p)]
+    lib.rtgrff_ctx_destroy.argtypes = [c_void_p]
+    lib.rtgrff_ctx_synchronize.argtypes = [c_void_p]
+    lib.rtgrff_ctx_launch_count.argtypes = [c_void_p]
+    lib.rtgrff_ctx_launch_count.restype = c_int64
+    lib.rtgrff_set_omega_cube.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, dp, c_int]
+    lib.rtgrff_set_field_cubes.argtypes = [c_void_p, fp, fp, fp, fp, fp, fp, c_int, c_int, c_int, dp]
+    lib.rtgrff_trace.argtypes = [c_void_p, c_int64, dp, dp, dp, dp, c_double, c_double, c_int64, c_int64, c_int,
+                                 c_double, c_int, dp, dp, POINTER(c_int64)]
+    lib.rtgrff_sample.argtypes = [c_void_p, c_int64, c_int64, fp, fp, fp, c_double, c_double, c_double, c_double,
+                                  fp, fp, fp, fp, POINTER(c_uint8)]
+    lib.rtgrff_sample_traced.argtypes = [c_void_p, fp, c_double, c_double, c_double, c_double, fp, fp, fp, fp,
+                                         POINTER(c_uint8), fp]
+    lib.PyGET_MW.argtypes = [ip, dp, dp, dp, dp, dp, dp]
+    lib.PyGET_MW.restype = c_int
+    lib.rtgrff_get_mw_slice.argtypes = [c_void_p, ip, dp, dp, dp, dp, dp, dp, ip]
+    lib.rtgrff_emission_traced.argtypes = [c_void_p, c_double, c_double, c_int, c_double, c_int, c_int, dp, dp]
+    lib.rtgrff_render_map.argtypes = [c_void_p, c_int64, dp, dp, dp, dp, c_int, POINTER(FreqParams), c_int, c_double,
+                                      c_double, c_double, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
+                                      POINTER(c_int64)]
+    for name in EXPORTS:
+        getattr(lib, name)          # AttributeError here = the .so is stale; rebuild it
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    """Map a C return code to the Python exception the reference raises in the same situation."""
+    if rc == RTGRFF_OK:
+        return
+    msg = load().rtgrff_last_error().decode(errors="replace")
+    if rc == RTGRFF_EINVAL:
+        raise ValueError(msg)
+    if rc == RTGRFF_ENOMEM:
+        raise MemoryError(msg)
+    if rc == RTGRFF_EUNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise RuntimeError(msg)
+
+
+def ptr(a, ctype):
+    return None if a is None else a.ctypes.data_as(POINTER(ctype))
+
+
+def f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def check_uniform_grid(grid, name):
+    """Grid validation of the reference (raytracingGRFF/gpu_raytrace.py:21-33): 1-D, >= 2 points,
+    uniform within max(1e-6*|step|, 1e-7*max(|g0|,|g_last|,1)); returns (g0, mean step)."""
+    g = np.asarray(grid, dtype=np.float64)
+    if g.ndim != 1 or g.size < 2:
+        raise ValueError(f"{name} must be 1D with at least 2 points")
+    d = np.diff(g)
+    step = float(np.mean(d))
+    if not np.isfinite(step) or step <= 0.0:
+        raise ValueError(f"{name} has invalid spacing")
+    max_dev = float(np.max(np.abs(d - step)))
+    tol = max(1e-6 * abs(step), 1e-7 * max(abs(g[0]), abs(g[-1]), 1.0))
+    if max_dev > tol:
+        raise ValueError(f"{name} must be uniformly spaced")
+    return float(g[0]), step
+
+
+def grid_geom(x_grid, y_grid, z_grid):
+    """geom[12] of include/rtgrff.h: per axis {g0, mean step, g_last, g1-g0}."""
+    out = np.empty(12, dtype=np.float64)
+    for a, (g, name) in enumerate(((x_grid, "x_grid"), (y_grid, "y_grid"), (z_grid, "z_grid"))):
+        g0, step = check_uniform_grid(g, name)
+        gg = np.asarray(g, dtype=np.float64)
+        out[4 * a: 4 * a + 4] = (g0, step, float(gg[-1]), float(gg[1] - gg[0]))
+    return out
+
+
+class Context:
+    """One GPU context (rtgrff_ctx).  `stream` is an int cudaStream_t handle (e.g.
+    ``torch.cuda.current_stream().cuda_stream``) or None for a library-owned stream."""
+
+    def __init__(self, device=0, stream=None):
+        lib = load()
+        n = lib.rtgrff_device_count()
+        if n <= 0:
+            raise RuntimeError("No CUDA device is available to raytracinggrff_b200 "
+                               f"({lib.rtgrff_last_error().decode(errors='replace') or 'device count 0'}); "
+                               "this package has no CPU path.")
+        h = c_void_p()
+        check(lib.rtgrff_ctx_create(int(device), c_void_p(stream) if stream else None, ctypes.byref(h)))
+        self._h = h
+        self.device = int(device)
+        self._lib = lib
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.rtgrff_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def handle(self):
+        if not self._h:
+            raise RuntimeError("context is closed")
+        return self._h
+
+    @property
+    def launch_count(self):
+        return int(self._lib.rtgrff_ctx_launch_count(self.handle))
+
+    def synchronize(self):
+        check(self._lib.rtgrff_ctx_synchronize(self.handle))
+
+
+_default_ctx = {}
+
+
+def default_context(device=0):
+    """Process-wide context per device, used by the module-level drop-in functions."""
+    ctx = _default_ctx.get(device)
+    if ctx is None or not ctx._h:
+        ctx = _default_ctx[device] = Context(device)
+    return ctx

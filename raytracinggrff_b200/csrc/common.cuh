@@ -1,0 +1,100 @@
+// Shared host/device definitions of librtgrff_b200 (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/rtgrff.h"
+
+namespace rtgrff {
+
+// build_rays.py:29-32 (C / R_S with the reference's rounded constants)
+constexpr double kC_R = 2.998e10 / 6.96e10;
+
+// Uniform-grid geometry of a cube.  x0/xl are the first/last node (scipy bounds test,
+// build_rays.py:140), inv_d = 1/mean step (gpu_raytrace.py:21-33).
+struct GridGeom {
+    int nx, ny, nz;
+    double x0, y0, z0;
+    double xl, yl, zl;
+    double idx, idy, idz;
+};
+
+// float32 view of the same geometry, rounded the way numpy's weak-scalar promotion rounds the
+// Python floats in gpu_raytrace.py:495-497, :646.
+struct GridGeomF {
+    int nx, ny, nz;
+    float x0, y0, z0;
+    float idx, idy, idz;
+};
+
+extern thread_local char g_err[512];
+
+inline int fail(int code, const char *fmt, ...)
+    __attribute__((format(printf, 2, 3)));
+
+#define RT_CUDA(call)                                                                          \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return rtgrff::fail(RTGRFF_ECUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call,     \
+                                cudaGetErrorString(e__));                                      \
+    } while (0)
+
+#define RT_TRY(call)                                                                           \
+    do {                                                                                       \
+        int r__ = (call);                                                                      \
+        if (r__ != RTGRFF_OK) return r__;                                                      \
+    } while (0)
+
+// Growable device buffer owned by a context.
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes);
+    void release();
+    template <class T> T *as() const { return static_cast<T *>(p); }
+};
+
+inline unsigned int blocks_for(int64_t n, int block)
+{
+    int64_t b = (n + block - 1) / block;
+    if (b < 1) b = 1;
+    return (unsigned int)b;
+}
+
+}  // namespace rtgrff
+
+struct rtgrff_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int64_t launches = 0;
+
+    // ray cube {omega_pe, d/dx, d/dy, d/dz}
+    rtgrff::DevBuf wcube;
+    rtgrff::GridGeom wgeom{};
+    bool has_wcube = false;
+
+    // field cubes {ne, te, |B|, 0} and {bx, by, bz, 0}
+    rtgrff::DevBuf fcube, bcube;
+    rtgrff::GridGeom fgeom{};
+    rtgrff::GridGeomF fgeomf{};
+    bool has_fcube = false, has_bvec = false;
+
+    // records of the last trace: positions SoA [rec][3][ray] f64, S [rec][ray] f64
+    rtgrff::DevBuf rec_pos, rec_s;
+    int64_t rec_n = 0, rec_rays = 0;
+    bool rec_has_s = false;
+
+    // samples of the last sample_traced: ne, te, b, ds, s float32 [rec][ray]; valid u8
+    rtgrff::DevBuf smp_ne, smp_te, smp_b, smp_ds, smp_s, smp_valid;
+    int64_t smp_n = 0, smp_rays = 0;
+
+    // scratch
+    rtgrff::DevBuf in0, in1, in2, in3, out0, out1, out2, out3, out4, out5, stage, counters;
+};

@@ -1,0 +1,172 @@
+// Fused map renderer for sm_100a: integrate the ray, sample n_e/T/|B| (and the B vector) at every
+// recorded step and advance the polarised transfer equation — one thread per (pixel, frequency),
+// nothing materialised: no r_record, no S array, no Parms.
+//
+// Equivalent to the reference chain
+//   trace_ray / ray_trace                      (build_rays.py:128-248)
+//   -> sample_model_with_rays                  (gpu_raytrace.py:632-651, float32 semantics)
+//   -> Parms packing + GET_MW + T_b conversion (script/resample_with_ray_tracing.py:467-530)
+// called once per frequency as the publication drivers do (script/pub/TbSpectra_gen.py:155-182).
+// A 2048^2 x 500-record map would need 25 GB of paths per frequency if materialised
+// (SURVEY.md §5); here a record lives in registers for the few hundred cycles it is needed.
+#pragma once
+
+#include "grff.cuh"
+#include "los_sampler.cuh"
+#include "ray_integrator.cuh"
+
+namespace rtgrff {
+
+struct FreqDev {
+    double nu, omega0, dt;
+    int64_t n_steps, stride;
+};
+
+struct MapArgs {
+    RayCube cube;
+    const float4 *fcube, *bcube;
+    GridGeomF fg;
+    int64_t n_rays;
+    const double *x_start, *y_start, *z_start, *kvec;
+    int n_freq;
+    const FreqDev *freqs;
+    double perturb_ratio, area;
+    float r_sun_cm, fill_ne, fill_te, fill_b;
+    int em_flag, s_max, use_bvec, order;
+    double *tb, *vi;                     // [freq][ray]
+    unsigned long long *active_steps;
+};
+
+// Transfer accumulated from the observer outwards (RTGRFF_ORDER_REVERSED): the records arrive
+// nearest-first, the radiation travels farthest-first.  I_obs = acc + M I_far with M a 2x2 matrix
+// in (L,R); folding one more (farther) operator I -> A I + b gives acc += M b, M = M A.
+struct OutwardTransfer {
+    double m00, m01, m10, m11, accL, accR;
+    Voxel prev;
+    bool have_prev;
+    __device__ __forceinline__ void init()
+    {
+        m00 = m11 = 1.0; m01 = m10 = 0.0; accL = accR = 0.0; have_prev = false; prev.ok = false;
+    }
+    __device__ __forceinline__ void fold(const DiagOp &d)
+    {
+        accL += m00 * d.bL + m01 * d.bR;
+        accR += m10 * d.bL + m11 * d.bR;
+        m00 *= d.aL; m10 *= d.aL; m01 *= d.aR; m11 *= d.aR;
+    }
+    __device__ __forceinline__ void fold_qt(double Q)
+    {
+        const double p = 1.0 - Q;
+        const double a = m00 * Q + m01 * p, b = m00 * p + m01 * Q;
+        const double c = m10 * Q + m11 * p, d = m10 * p + m11 * Q;
+        m00 = a; m01 = b; m10 = c; m11 = d;
+    }
+    __device__ __forceinline__ void push(double nu, const Voxel &v)
+    {
+        if (!v.ok) { have_prev = false; return; }
+        if (have_prev && prev.B > 0.0 && v.B > 0.0) {
+            // radiation crosses v -> prev: between_voxels(v, prev) lists the events in that order,
+            // folding outwards meets them last-first.
+            const Between b = between_voxels(nu, v, prev);
+            fold(b.after);
+            if (b.qt) fold_qt(b.Q);
+            fold(b.before);
+        }
+        fold(voxel_op(nu, v));
+        prev = v;
+        have_prev = true;
+    }
+};
+
+template <bool CS, bool LERP64>
+__global__ void __launch_bounds__(128) render_map_kernel(const MapArgs a)
+{
+    const int64_t ray = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int fi = blockIdx.y;
+    const bool has_ray = ray < a.n_rays;
+    const RayCube &C = a.cube;
+    const FreqDev fp = a.freqs[fi];
+
+    State s;
+    s.rx = s.ry = s.rz = s.kx = s.ky = s.kz = nan("");
+    float sx0 = 0.f, sy0 = 0.f, sz0 = 0.f;   // ray_start as float32 (gpu_raytrace.py:650)
+    if (has_ray) {
+        s.rx = a.x_start[ray]; s.ry = a.y_start[ray]; s.rz = a.z_start[ray];
+        sx0 = (float)s.rx; sy0 = (float)s.ry; sz0 = (float)s.rz;
+        const double kc0 = start_kc(C, s.rx, s.ry, s.rz, fp.omega0);
+        if (a.kvec) {
+            s.kx = a.kvec[ray * 3 + 0] * kc0; s.ky = a.kvec[ray * 3 + 1] * kc0; s.kz = a.kvec[ray * 3 + 2] * kc0;
+        } else {
+            s.kx = 0.0 * kc0; s.ky = 0.0 * kc0; s.kz = -kc0;
+        }
+    }
+    bool alive = has_ray;
+    double s_step = CS ? 0.0 : 1.0;
+    unsigned long long moved_steps = 0;
+    int64_t next_rec = 0;
+
+    OnlineTransfer<1> fwd;
+    OutwardTransfer rev;
+    fwd.init();
+    rev.init();
+    float px = sx0, py = sy0, pz = sz0;   // previous VALID sample position (float32)
+    bool first = true;
+    bool tail_done = false;               // a frozen ray repeats the same record: ds = 0 -> empty voxel
+
+    for (int64_t i = 0; i < fp.n_steps; ++i) {
+        if (alive) {
+            const State s0 = s;
+            s = rk4_step<LERP64>(C, s0, fp.dt);
+            if (CS) s_step = cross_section_ratio<LERP64>(C, s0, s, fp.dt, a.perturb_ratio);
+            const bool moved = in_cube(C, s0.rx, s0.ry, s0.rz) && state_differs(s, s0);
+            moved_steps += moved ? 1ull : 0ull;
+            alive = moved;
+        }
+        if (i == next_rec) {
+            next_rec += fp.stride;
+            if (has_ray && !tail_done) {
+                // --- sampler (float32, gpu_raytrace.py:642-650) ---
+                const float x = (float)s.rx, y = (float)s.ry, z = (float)s.rz, sv = (float)s_step;
+                if (sample_valid(x, y, z, sv)) {
+                    const FieldSample f = sample_fields(a.fcube, a.fg, x, y, z, a.fill_ne, a.fill_te, a.fill_b);
+                    const float dist = first ? dist_first_np(x, y, z, px, py, pz) : dist_np(x, y, z, px, py, pz);
+                    const float ds = __fmul_rn(dist, a.r_sun_cm);
+                    // --- Parms packing rules (script/resample_with_ray_tracing.py:472-501) ---
+                    if (isfinite(f.ne) && isfinite(f.te) && isfinite(f.b)) {
+                        double th = 90.0, bmag = (double)f.b;
+                        if (a.use_bvec) {
+                            const float3 bv = sample_bvec(a.bcube, a.fg, x, y, z);
+                            const double dx = (double)x - (double)px, dy = (double)y - (double)py, dz = (double)z - (double)pz;
+                            const double dn = sqrt(dx * dx + dy * dy + dz * dz);
+                            bmag = sqrt((double)bv.x * bv.x + (double)bv.y * bv.y + (double)bv.z * bv.z);
+                            // radiation propagates towards the observer: against the tracing direction
+                            const double c = -((double)bv.x * dx + (double)bv.y * dy + (double)bv.z * dz) / (bmag * dn);
+                            th = (bmag > 0.0 && dn > 0.0) ? acos(fmin(1.0, fmax(-1.0, c))) * (180.0 / kPi) : 90.0;
+                        }
+                        const Voxel v = make_voxel((double)ds, (double)f.te, (double)f.ne, bmag, th, a.em_flag, a.s_max);
+                        if (a.order == RTGRFF_ORDER_RECORD) fwd.push(fp.nu, v);
+                        else rev.push(fp.nu, v);
+                    }
+                    px = x; py = y; pz = z;
+                    first = false;
+                }
+                // once frozen, every later record repeats this one (ds = 0 or invalid): nothing to add
+                if (!alive) tail_done = true;
+            }
+        }
+        if (!__any_sync(0xffffffffu, alive)) break;
+    }
+    if (has_ray) {
+        double tb, vi;
+        if (a.order == RTGRFF_ORDER_RECORD) tb_vi(fwd.st.L[0], fwd.st.R[0], fp.nu, a.area, tb, vi);
+        else tb_vi(rev.accL, rev.accR, fp.nu, a.area, tb, vi);
+        a.tb[(size_t)fi * a.n_rays + ray] = tb;
+        a.vi[(size_t)fi * a.n_rays + ray] = vi;
+    }
+    if (a.active_steps) {
+        for (int off = 16; off > 0; off >>= 1) moved_steps += __shfl_down_sync(0xffffffffu, moved_steps, off);
+        if ((threadIdx.x & 31) == 0 && moved_steps) atomicAdd(a.active_steps, moved_steps);
+    }
+}
+
+}  // namespace rtgrff

@@ -1,0 +1,403 @@
+// GRFF-style emission/transfer for sm_100a: free-free + gyroresonance emissivity/absorption per
+// magneto-ionic mode and the transfer equation along one line of sight, FP64.
+//
+// Replaces the external GRFF_DEM_Transfer.so::PyGET_MW the reference binds at
+// script/resample_with_ray_tracing.py:79-86 and calls per pixel at :502-509 (and
+// script/synthetic_FF_map_single_thread.py:208), and fastGRFF.get_mw_slice (:443-446).  The
+// source of either is NOT in the reference tree; the physics here follows the published
+// formulation (Fleishman, Kuznetsov & Landi 2021; Fleishman & Kuznetsov 2010 App. A; Dulk 1985)
+// as specified in DESIGN.md §GRFF — parity for this stage is against oracle/oracle_grff.c and
+// analytic limits ("parity unpinned" against the real binary).
+//
+// Three consumers share the device functions: the warp-per-(pixel,frequency) kernel behind the
+// PyGET_MW / get_mw_slice ABIs (lanes over voxels, warp-shuffle composition of the per-voxel
+// affine maps), the thread-per-ray kernel on sampler output, and the fused map kernel.
+#pragma once
+
+#include "common.cuh"
+
+namespace rtgrff {
+
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kKff = 9.76981314722991795e-03;      // 8 e^6 / (3 sqrt(2 pi) c (m k)^1.5)
+constexpr double kCqt = 1.45534837532918656e+17;      // e^5 / (32 pi^2 m^4 c^4)
+constexpr double kNup2 = 8.06163860001142621e+07;     // e^2 / (pi m):  nu_p^2 = kNup2 n_e
+constexpr double kNuB = 2.79924898723330395e+06;      // e / (2 pi m c): nu_B = kNuB B
+constexpr double kBres = 3.57238675287821001e-07;     // 2 pi m c / e:  B_res = kBres nu / s
+constexpr double kGrPref = 2.65400885457447444e-02;   // pi e^2 / (m c)
+constexpr double kKbC2 = 1.53617918724037216e-37;     // k_B / c^2
+constexpr double kBeta2 = 1.68637005266055143e-10;    // k_B / (m c^2)
+constexpr double kZeta = 1.14529914529914545e+00;     // sum Z^2 n_i / n_e, H + He (He/H = 0.085)
+constexpr double kAu = 1.495978707e13;
+constexpr double kSfu = 1e-19;
+
+struct Voxel {
+    double dz, T, ne, B, th, cth, sth;
+    int smax;
+    bool gr_on, ff_on, ok;
+};
+
+struct Mode {
+    double n2, kap, src;
+    bool prop;
+};
+
+// I' = a I + b on the L and R slots.
+struct DiagOp {
+    double aL, aR, bL, bR;
+};
+
+__device__ __forceinline__ DiagOp diag_identity() { return DiagOp{1.0, 1.0, 0.0, 0.0}; }
+
+// second o first
+__device__ __forceinline__ DiagOp diag_then(const DiagOp &first, const DiagOp &second)
+{
+    return DiagOp{first.aL * second.aL, first.aR * second.aR, fma(first.bL, second.aL, second.bL),
+                  fma(first.bR, second.aR, second.bR)};
+}
+
+__device__ __forceinline__ Voxel make_voxel(double dz, double T, double ne, double B, double th_deg,
+                                            int flag, int smax)
+{
+    Voxel v;
+    v.dz = dz; v.T = T; v.ne = ne; v.B = B;
+    v.th = th_deg * (kPi / 180.0);
+    v.smax = smax;
+    v.gr_on = !(flag & 1);
+    v.ff_on = !(flag & 2);
+    v.ok = (dz > 0.0) && (T > 0.0) && (ne > 0.0) && (B >= 0.0) && isfinite(dz) && isfinite(T) &&
+           isfinite(ne) && isfinite(B) && isfinite(v.th);
+    v.cth = 1.0; v.sth = 0.0;
+    if (v.ok) sincos(v.th, &v.sth, &v.cth);
+    return v;
+}
+
+// Refractive index, free-free opacity and Kirchhoff source of mode sg (-1 X, +1 O).
+template <bool WANT_POL>
+__device__ __forceinline__ Mode mode_eval(double nu, double ne, double B, double T, double cth, double sth,
+                                          int sg, bool ff_on, double &Tpol, double &Lpol)
+{
+    Mode m;
+    m.prop = false; m.kap = 0.0; m.src = 0.0; m.n2 = 0.0;
+    Tpol = 0.0; Lpol = 0.0;
+    const double nuB = kNuB * B;
+    const double u = (nuB / nu) * (nuB / nu), v = kNup2 * ne / (nu * nu);
+    const double s2 = sth * sth, c2 = cth * cth;
+    double F = 1.0, n2;
+    if (u > 0.0) {
+        if (sg < 0 && (u >= 1.0 || v >= 1.0 - sqrt(u))) return m;   // X cutoff / nu <= nu_B
+        if (sg > 0 && v >= 1.0) return m;                            // O cutoff
+        const double omv = 1.0 - v;
+        const double D = u * u * s2 * s2 + 4.0 * u * omv * omv * c2;
+        const double sD = sg * sqrt(D);
+        const double den = 2.0 * omv - u * s2 + sD;
+        n2 = 1.0 - 2.0 * v * omv / den;
+        F = 2.0 * (sD * (u * s2 + 2.0 * omv * omv) - u * u * s2 * s2) / (sD * den * den);
+        if (WANT_POL) {
+            const double su = sqrt(u);
+            Tpol = 2.0 * su * omv * cth / (u * s2 - sD);
+            Lpol = (v * su * sth + Tpol * u * v * sth * cth) / (1.0 - u - v + u * v * c2);
+        }
+    } else {
+        if (v >= 1.0) return m;
+        n2 = 1.0 - v;
+    }
+    if (!(n2 > 0.0) || !isfinite(n2) || !isfinite(F)) return m;
+    m.prop = true;
+    m.n2 = n2;
+    m.src = n2 * nu * nu * kKbC2 * T;
+    if (ff_on && ne > 0.0) {
+        const double lnL = (T < 2e5) ? 18.2 + 1.5 * log(T) - log(nu) : 24.573 + log(T / nu);
+        double kap = kKff * ne * ne * kZeta * lnL * F / (sqrt(n2) * nu * nu * T * sqrt(T));
+        if (!(kap > 0.0) || !isfinite(kap)) kap = 0.0;
+        m.kap = kap;
+    }
+    return m;
+}
+
+// slab of optical depth tau and source src as an affine map; evanescent -> I = 0.
+__device__ __forceinline__ void slab_ab(bool prop, double tau, double src, double &a, double &b)
+{
+    if (!prop) { a = 0.0; b = 0.0; return; }
+    if (tau > 0.0) {
+        const double em = -expm1(-tau);
+        a = 1.0 - em; b = src * em;
+    } else {
+        a = 1.0; b = 0.0;
+    }
+}
+
+// Uniform slab of one voxel.
+__device__ __forceinline__ DiagOp voxel_op(double nu, const Voxel &v)
+{
+    double tp, lp, aX, bX, aO, bO;
+    const Mode mx = mode_eval<false>(nu, v.ne, v.B, v.T, v.cth, v.sth, -1, v.ff_on, tp, lp);
+    const Mode mo = mode_eval<false>(nu, v.ne, v.B, v.T, v.cth, v.sth, +1, v.ff_on, tp, lp);
+    slab_ab(mx.prop, mx.kap * v.dz, mx.src, aX, bX);
+    slab_ab(mo.prop, mo.kap * v.dz, mo.src, aO, bO);
+    // X is R where cos(theta) >= 0
+    return (v.cth >= 0.0) ? DiagOp{aO, aX, bO, bX} : DiagOp{aX, aO, bX, bO};
+}
+
+// One gyroresonance layer nu = s nu_B at interpolated plasma parameters.
+__device__ __forceinline__ DiagOp gr_layer_op(double nu, int s, double ne, double T, double th, double LB)
+{
+    double sth, cth;
+    sincos(th, &sth, &cth);
+    const double Bres = kBres * nu / (double)s;
+    double a[2], b[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int sg = q == 0 ? -1 : 1;
+        double Ts, Ls;
+        const Mode m = mode_eval<true>(nu, ne, Bres, T, cth, sth, sg, false, Ts, Ls);
+        double tau = 0.0;
+        if (m.prop) {
+            const double lg = 2.0 * s * log((double)s) - (s - 1) * 0.69314718055994530942 - lgamma(s + 1.0) +
+                              (s - 1) * log(kBeta2 * T * sth * sth) + (s - 1.5) * log(m.n2);
+            const double pol = Ts * cth + Ls * sth + 1.0;
+            tau = kGrPref * ne * LB / nu * exp(lg) * pol * pol / (1.0 + Ts * Ts);
+            if (!(tau > 0.0) || !isfinite(tau)) tau = 0.0;
+        }
+        slab_ab(m.prop, tau, m.src, a[q], b[q]);
+    }
+    return (cth >= 0.0) ? DiagOp{a[1], a[0], b[1], b[0]} : DiagOp{a[0], a[1], b[0], b[1]};
+}
+
+// Everything that happens between the centres of two consecutive non-empty voxels p -> k:
+// gyroresonance layers (diagonal in L/R) before and after an optional quasi-transverse layer.
+struct Between {
+    DiagOp before, after;
+    double Q;     // exact-coupling transmission exp(-delta)
+    bool qt;
+};
+
+__device__ __forceinline__ Between between_voxels(double nu, const Voxel &p, const Voxel &k)
+{
+    Between o;
+    o.before = diag_identity(); o.after = diag_identity(); o.Q = 1.0;
+    o.qt = (p.cth * k.cth < 0.0);
+    const double dzm = 0.5 * (p.dz + k.dz);
+    double tqt = 2.0;
+    if (o.qt) {
+        tqt = (0.5 * kPi - p.th) / (k.th - p.th);
+        const double g = fabs(k.th - p.th) / dzm;
+        const double nav = 0.5 * (p.ne + k.ne), Bav = 0.5 * (p.B + k.B);
+        o.Q = exp(-kCqt * nav * Bav * Bav * Bav / (nu * nu * nu * nu * g));
+    }
+    if (p.gr_on && k.gr_on && p.B != k.B) {
+        const int smax = min(p.smax, k.smax);
+        const bool up = k.B > p.B;
+        const double blo = fmin(p.B, k.B), bhi = fmax(p.B, k.B);
+        // harmonics whose resonant field lies strictly inside (blo, bhi): s in (kBres nu/bhi, kBres nu/blo);
+        // the range is taken one wider than that and the sign test below decides.
+        const double sn = kBres * nu;
+        const double lo_d = floor(sn / bhi), hi_d = (blo > 0.0) ? ceil(sn / blo) : (double)smax;
+        const int s_lo = lo_d > 2.0 ? (lo_d < (double)smax ? (int)lo_d : smax + 1) : 2;
+        const int s_hi = hi_d < (double)smax ? (int)hi_d : smax;
+        for (int q = s_lo; q <= s_hi; ++q) {
+            const int s = up ? (s_hi + s_lo - q) : q;   // path order: B rising -> high harmonics first
+            const double Bres = sn / (double)s;
+            if (!((p.B - Bres) * (k.B - Bres) < 0.0)) continue;
+            const double t = (Bres - p.B) / (k.B - p.B);
+            const DiagOp g = gr_layer_op(nu, s, p.ne + t * (k.ne - p.ne), p.T + t * (k.T - p.T),
+                                         p.th + t * (k.th - p.th), Bres * dzm / fabs(k.B - p.B));
+            if (t >= tqt) o.after = diag_then(o.after, g);
+            else o.before = diag_then(o.before, g);
+        }
+    }
+    return o;
+}
+
+// Polarisation state for the three mode-coupling variants GRFF reports:
+// {L,R} weak (RL[1],RL[2]), strong (RL[3],RL[4]), exact (RL[5],RL[6]).
+template <int NVAR>
+struct PolState {
+    double L[NVAR], R[NVAR];   // NVAR = 3: weak, strong, exact;  NVAR = 1: exact only
+    __device__ __forceinline__ void clear()
+    {
+#pragma unroll
+        for (int q = 0; q < NVAR; ++q) { L[q] = 0.0; R[q] = 0.0; }
+    }
+    __device__ __forceinline__ void apply(const DiagOp &d)
+    {
+#pragma unroll
+        for (int q = 0; q < NVAR; ++q) { L[q] = fma(L[q], d.aL, d.bL); R[q] = fma(R[q], d.aR, d.bR); }
+    }
+    __device__ __forceinline__ void qt(double Q)
+    {
+        const int e = NVAR - 1;
+        const double l = L[e], r = R[e];
+        L[e] = Q * l + (1.0 - Q) * r;
+        R[e] = Q * r + (1.0 - Q) * l;
+        if (NVAR == 3) { const double t = L[0]; L[0] = R[0]; R[0] = t; }
+    }
+    __device__ __forceinline__ void apply(const Between &b)
+    {
+        apply(b.before);
+        if (b.qt) qt(b.Q);
+        apply(b.after);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Kernel A: Parms ABI.  One warp per (pixel, frequency); lanes over voxels in chunks of 32.
+// Each lane turns its voxel (and the interval before it) into an affine map, the warp composes
+// the 32 maps in path order with shuffles, lane 0 carries the polarisation state.
+// Parms (15, Nz) column-major per pixel: element (m,k) at k*15+m  (script/...:489-501).
+// ---------------------------------------------------------------------------------------------
+struct SliceArgs {
+    const double *parms;    // (15, Nz, Npix)
+    const double *rparms;   // (3, Npix)
+    double *rl;             // (7, Nf, Npix)
+    int32_t *status;        // (Npix) or nullptr
+    int npix, nz, nf;
+};
+
+__device__ __forceinline__ Voxel load_voxel(const double *P)
+{
+    return make_voxel(P[0], P[1], P[2], P[3], P[4], (int)P[6], (int)P[7]);
+}
+
+__device__ __forceinline__ DiagOp shfl_down_op(const DiagOp &d, int off)
+{
+    return DiagOp{__shfl_down_sync(0xffffffffu, d.aL, off), __shfl_down_sync(0xffffffffu, d.aR, off),
+                  __shfl_down_sync(0xffffffffu, d.bL, off), __shfl_down_sync(0xffffffffu, d.bR, off)};
+}
+
+__global__ void __launch_bounds__(128) grff_slice_kernel(const SliceArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= (int64_t)a.npix * a.nf) return;
+    const int pix = (int)(warp / a.nf), f = (int)(warp % a.nf);
+    const double *R = a.rparms + (size_t)pix * 3;
+    const double nu = R[1] * pow(10.0, R[2] * (double)f);
+    const double *P = a.parms + (size_t)pix * 15 * a.nz;
+    PolState<3> st;
+    st.clear();
+    for (int base = 0; base < a.nz; base += 32) {
+        const int k = base + lane;
+        DiagOp op = diag_identity();
+        Between bt;
+        bt.qt = false;
+        bool has_bt = false;
+        if (k < a.nz) {
+            const Voxel v = load_voxel(P + (size_t)k * 15);
+            if (v.ok) {
+                if (k > 0) {
+                    const Voxel pv = load_voxel(P + (size_t)(k - 1) * 15);
+                    if (pv.ok && pv.B > 0.0 && v.B > 0.0) { bt = between_voxels(nu, pv, v); has_bt = true; }
+                }
+                op = voxel_op(nu, v);
+            }
+        }
+        const bool any_qt = __any_sync(0xffffffffu, has_bt && bt.qt);
+        if (!any_qt) {
+            if (has_bt) op = diag_then(diag_then(bt.before, bt.after), op);
+            // ordered composition: after the loop lane 0 holds op_31 o ... o op_0
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const DiagOp nx = shfl_down_op(op, off);
+                if (lane + off < 32) op = diag_then(op, nx);
+            }
+            if (lane == 0) st.apply(op);
+        } else {
+            // a quasi-transverse layer mixes L and R: replay this chunk in order on lane 0's state
+            for (int l = 0; l < 32; ++l) {
+                Between b;
+                b.before = DiagOp{__shfl_sync(0xffffffffu, bt.before.aL, l), __shfl_sync(0xffffffffu, bt.before.aR, l),
+                                  __shfl_sync(0xffffffffu, bt.before.bL, l), __shfl_sync(0xffffffffu, bt.before.bR, l)};
+                b.after = DiagOp{__shfl_sync(0xffffffffu, bt.after.aL, l), __shfl_sync(0xffffffffu, bt.after.aR, l),
+                                 __shfl_sync(0xffffffffu, bt.after.bL, l), __shfl_sync(0xffffffffu, bt.after.bR, l)};
+                b.Q = __shfl_sync(0xffffffffu, bt.Q, l);
+                b.qt = __shfl_sync(0xffffffffu, (int)bt.qt, l) != 0;
+                const bool hb = __shfl_sync(0xffffffffu, (int)has_bt, l) != 0;
+                const DiagOp o = DiagOp{__shfl_sync(0xffffffffu, op.aL, l), __shfl_sync(0xffffffffu, op.aR, l),
+                                        __shfl_sync(0xffffffffu, op.bL, l), __shfl_sync(0xffffffffu, op.bR, l)};
+                if (lane == 0) {
+                    if (hb) st.apply(b);
+                    st.apply(o);
+                }
+            }
+        }
+    }
+    if (lane == 0) {
+        double *o = a.rl + ((size_t)pix * a.nf + f) * 7;
+        const double to_sfu = R[0] / (kAu * kAu) / kSfu;
+        o[0] = nu / 1e9;
+        o[1] = st.L[0] * to_sfu; o[2] = st.R[0] * to_sfu;
+        o[3] = st.L[1] * to_sfu; o[4] = st.R[1] * to_sfu;
+        o[5] = st.L[2] * to_sfu; o[6] = st.R[2] * to_sfu;
+        if (a.status && f == 0) a.status[pix] = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Online transfer used by the thread-per-ray consumers (sampler output, fused map).
+// Feeds voxels one at a time in path order; keeps the previous non-empty voxel for the
+// between-voxel events.  Mirrors the packing rules of script/resample_with_ray_tracing.py:472-501:
+// only samples with valid & finite(ne,te,b) are handed over, theta = 90 deg unless given.
+// ---------------------------------------------------------------------------------------------
+template <int NVAR>
+struct OnlineTransfer {
+    PolState<NVAR> st;
+    Voxel prev;
+    bool have_prev;
+    __device__ __forceinline__ void init() { st.clear(); have_prev = false; prev.ok = false; }
+    __device__ __forceinline__ void push(double nu, const Voxel &v)
+    {
+        if (!v.ok) { have_prev = false; return; }
+        if (have_prev && prev.B > 0.0 && v.B > 0.0) st.apply(between_voxels(nu, prev, v));
+        st.apply(voxel_op(nu, v));
+        prev = v;
+        have_prev = true;
+    }
+};
+
+// T_b and V/I from L,R intensities exactly as the workflow converts GRFF's SFU output
+// (script/resample_with_ray_tracing.py:91-94, :513-520, :530): the library-side flux uses kAu/kSfu,
+// the workflow-side conversion its own rounded constants.
+__device__ __forceinline__ void tb_vi(double IL, double IR, double nu, double area, double &tb, double &vi)
+{
+    const double to_sfu = area / (kAu * kAu) / kSfu;
+    const double l = IL * to_sfu, r = IR * to_sfu;
+    const double conv = (1e-19 * 2.998e10 * 2.998e10 / (2.0 * 1.38065e-16 * nu * nu) / area) * (1.49599e13 * 1.49599e13);
+    tb = (l + r) * conv;
+    vi = (l - r) / (l + r + 1e-30);
+    if (!isfinite(tb)) tb = 0.0;   // np.nan_to_num(emission_cube, nan=0, posinf=0, neginf=0)
+}
+
+struct EmissionArgs {
+    const float *ne, *te, *b, *ds;   // [rec][ray]
+    const uint8_t *valid;
+    int64_t n_rec, n_rays;
+    double area, freq0, log_step;
+    int n_freq, em_flag, s_max;
+    double *tb, *vi;                 // (ray, freq)
+};
+
+// Thread per (ray, frequency) on sampler output (staged pipeline).
+__global__ void __launch_bounds__(128) emission_rays_kernel(const EmissionArgs a)
+{
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= a.n_rays * a.n_freq) return;
+    const int64_t ray = q % a.n_rays;
+    const int f = (int)(q / a.n_rays);
+    const double nu = a.freq0 * pow(10.0, a.log_step * (double)f);
+    OnlineTransfer<1> tr;
+    tr.init();
+    for (int64_t rec = 0; rec < a.n_rec; ++rec) {
+        const size_t o = (size_t)rec * a.n_rays + ray;
+        if (!a.valid[o]) continue;
+        const float ne = a.ne[o], te = a.te[o], b = a.b[o];
+        if (!(isfinite(ne) && isfinite(te) && isfinite(b))) continue;
+        tr.push(nu, make_voxel((double)a.ds[o], (double)te, (double)ne, (double)b, 90.0, a.em_flag, a.s_max));
+    }
+    double tb, vi;
+    tb_vi(tr.st.L[0], tr.st.R[0], nu, a.area, tb, vi);
+    a.tb[(size_t)ray * a.n_freq + f] = tb;
+    a.vi[(size_t)ray * a.n_freq + f] = vi;
+}
+
+}  // namespace rtgrff

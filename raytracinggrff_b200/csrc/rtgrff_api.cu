@@ -1,0 +1,520 @@
+// C-ABI of librtgrff_b200.so (declared in include/rtgrff.h).  Host-side staging + launches only;
+// the kernels live in the .cuh files next to this one.
+#include <stdarg.h>
+
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "fused_map.cuh"
+#include "grff.cuh"
+#include "los_sampler.cuh"
+#include "ray_integrator.cuh"
+
+namespace rtgrff {
+
+thread_local char g_err[512] = "";
+
+inline int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int DevBuf::reserve(size_t bytes)
+{
+    if (bytes <= cap) return RTGRFF_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+        p = nullptr;
+        return fail(e == cudaErrorMemoryAllocation ? RTGRFF_ENOMEM : RTGRFF_ECUDA, "cudaMalloc(%zu) -> %s", bytes,
+                    cudaGetErrorString(e));
+    }
+    cap = bytes;
+    return RTGRFF_OK;
+}
+
+void DevBuf::release()
+{
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+}
+
+static int geom_from(const double g[12], int nx, int ny, int nz, GridGeom &o)
+{
+    if (nx < 2 || ny < 2 || nz < 2) return fail(RTGRFF_EINVAL, "cube needs >= 2 points per axis (%d,%d,%d)", nx, ny, nz);
+    if ((int64_t)nx * ny * nz >= (int64_t)1 << 31) return fail(RTGRFF_EINVAL, "cube larger than 2^31 voxels");
+    for (int a = 0; a < 3; ++a)
+        if (!(g[4 * a + 1] > 0.0) || !isfinite(g[4 * a + 1])) return fail(RTGRFF_EINVAL, "axis %d has invalid spacing", a);
+    o.nx = nx; o.ny = ny; o.nz = nz;
+    o.x0 = g[0]; o.idx = 1.0 / g[1]; o.xl = g[2];
+    o.y0 = g[4]; o.idy = 1.0 / g[5]; o.yl = g[6];
+    o.z0 = g[8]; o.idz = 1.0 / g[9]; o.zl = g[10];
+    return RTGRFF_OK;
+}
+
+static RayCube ray_cube_of(const rtgrff_ctx *c)
+{
+    RayCube r;
+    const GridGeom &g = c->wgeom;
+    r.c = c->wcube.as<float4>();
+    r.nx = g.nx; r.ny = g.ny; r.nz = g.nz;
+    r.sy = g.nz; r.sx = g.ny * g.nz;
+    r.x0 = g.x0; r.y0 = g.y0; r.z0 = g.z0;
+    r.xl = g.xl; r.yl = g.yl; r.zl = g.zl;
+    r.idx = g.idx; r.idy = g.idy; r.idz = g.idz;
+    return r;
+}
+
+static int use(rtgrff_ctx *c)
+{
+    if (!c) return fail(RTGRFF_EINVAL, "null context");
+    RT_CUDA(cudaSetDevice(c->device));
+    return RTGRFF_OK;
+}
+
+static int h2d(rtgrff_ctx *c, DevBuf &b, const void *src, size_t bytes)
+{
+    RT_TRY(b.reserve(bytes ? bytes : 1));
+    if (bytes) RT_CUDA(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    return RTGRFF_OK;
+}
+
+static int d2h(rtgrff_ctx *c, void *dst, const void *src, size_t bytes)
+{
+    if (bytes) RT_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    return RTGRFF_OK;
+}
+
+static int launched(rtgrff_ctx *c, const char *what)
+{
+    c->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(RTGRFF_ECUDA, "launch %s -> %s", what, cudaGetErrorString(e));
+    return RTGRFF_OK;
+}
+
+static int trace_variant()
+{
+    // RTGRFF_LERP64=1 selects FP64 trilinear arithmetic (default: FP32 lerps on the FP32 cube).
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("RTGRFF_LERP64");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v;
+}
+
+}  // namespace rtgrff
+
+using namespace rtgrff;
+
+extern "C" {
+
+const char *rtgrff_version(void) { return "rtgrff_b200 0.1.0 sm_100a"; }
+const char *rtgrff_last_error(void) { return g_err; }
+
+int rtgrff_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return fail(RTGRFF_ECUDA, "cudaGetDeviceCount -> %s", cudaGetErrorString(e));
+    return n;
+}
+
+int rtgrff_ctx_create(int device, void *stream, rtgrff_ctx **out)
+{
+    if (!out) return fail(RTGRFF_EINVAL, "out is null");
+    *out = nullptr;
+    int n = 0;
+    RT_CUDA(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) return fail(RTGRFF_EINVAL, "device %d out of range (%d visible)", device, n);
+    RT_CUDA(cudaSetDevice(device));
+    rtgrff_ctx *c = new (std::nothrow) rtgrff_ctx();
+    if (!c) return fail(RTGRFF_ENOMEM, "out of host memory");
+    c->device = device;
+    cudaDeviceProp prop;
+    RT_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+    } else {
+        RT_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    *out = c;
+    return RTGRFF_OK;
+}
+
+int rtgrff_ctx_destroy(rtgrff_ctx *c)
+{
+    if (!c) return RTGRFF_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    DevBuf *bufs[] = {&c->wcube, &c->fcube, &c->bcube, &c->rec_pos, &c->rec_s, &c->smp_ne, &c->smp_te, &c->smp_b,
+                      &c->smp_ds, &c->smp_s, &c->smp_valid, &c->in0, &c->in1, &c->in2, &c->in3, &c->out0, &c->out1,
+                      &c->out2, &c->out3, &c->out4, &c->out5, &c->stage, &c->counters};
+    for (DevBuf *b : bufs) b->release();
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return RTGRFF_OK;
+}
+
+int rtgrff_ctx_synchronize(rtgrff_ctx *c)
+{
+    RT_TRY(use(c));
+    RT_CUDA(cudaStreamSynchronize(c->stream));
+    return RTGRFF_OK;
+}
+
+int64_t rtgrff_ctx_launch_count(const rtgrff_ctx *c) { return c ? c->launches : 0; }
+
+int rtgrff_set_omega_cube(rtgrff_ctx *c, const double *omega_pe, int nx, int ny, int nz, const double geom[12],
+                          int on_device)
+{
+    RT_TRY(use(c));
+    if (!omega_pe || !geom) return fail(RTGRFF_EINVAL, "null argument");
+    GridGeom g;
+    RT_TRY(geom_from(geom, nx, ny, nz, g));
+    const size_t nvox = (size_t)nx * ny * nz;
+    const double *src = omega_pe;
+    if (!on_device) {
+        RT_TRY(h2d(c, c->stage, omega_pe, nvox * sizeof(double)));
+        src = c->stage.as<double>();
+    }
+    RT_TRY(c->wcube.reserve(nvox * sizeof(float4)));
+    build_ray_cube_kernel<<<blocks_for((int64_t)nvox, 256), 256, 0, c->stream>>>(src, c->wcube.as<float4>(), nx, ny, nz,
+                                                                                 geom[3], geom[7], geom[11]);
+    RT_TRY(launched(c, "build_ray_cube_kernel"));
+    c->wgeom = g;
+    c->has_wcube = true;
+    RT_CUDA(cudaStreamSynchronize(c->stream));   // the host buffer may be reused by the caller
+    return RTGRFF_OK;
+}
+
+int rtgrff_set_field_cubes(rtgrff_ctx *c, const float *ne, const float *te, const float *b, const float *bx,
+                           const float *by, const float *bz, int nx, int ny, int nz, const double geom[12])
+{
+    RT_TRY(use(c));
+    if (!ne || !te || !b || !geom) return fail(RTGRFF_EINVAL, "null argument");
+    const bool bvec = bx && by && bz;
+    if ((bx || by || bz) && !bvec) return fail(RTGRFF_EINVAL, "bx, by, bz must be given together");
+    GridGeom g;
+    RT_TRY(geom_from(geom, nx, ny, nz, g));
+    const size_t nvox = (size_t)nx * ny * nz, fb = nvox * sizeof(float);
+    RT_TRY(c->stage.reserve(3 * fb));
+    float *s0 = c->stage.as<float>(), *s1 = s0 + nvox, *s2 = s1 + nvox;
+    RT_TRY(c->fcube.reserve(nvox * sizeof(float4)));
+    RT_CUDA(cudaMemcpyAsync(s0, ne, fb, cudaMemcpyHostToDevice, c->stream));
+    RT_CUDA(cudaMemcpyAsync(s1, te, fb, cudaMemcpyHostToDevice, c->stream));
+    RT_CUDA(cudaMemcpyAsync(s2, b, fb, cudaMemcpyHostToDevice, c->stream));
+    interleave3_kernel<<<blocks_for((int64_t)nvox, 256), 256, 0, c->stream>>>(s0, s1, s2, c->fcube.as<float4>(), (int64_t)nvox);
+    RT_TRY(launched(c, "interleave3_kernel"));
+    if (bvec) {
+        RT_TRY(c->bcube.reserve(nvox * sizeof(float4)));
+        RT_CUDA(cudaMemcpyAsync(s0, bx, fb, cudaMemcpyHostToDevice, c->stream));
+        RT_CUDA(cudaMemcpyAsync(s1, by, fb, cudaMemcpyHostToDevice, c->stream));
+        RT_CUDA(cudaMemcpyAsync(s2, bz, fb, cudaMemcpyHostToDevice, c->stream));
+        interleave3_kernel<<<blocks_for((int64_t)nvox, 256), 256, 0, c->stream>>>(s0, s1, s2, c->bcube.as<float4>(), (int64_t)nvox);
+        RT_TRY(launched(c, "interleave3_kernel"));
+    }
+    c->fgeom = g;
+    GridGeomF &f = c->fgeomf;
+    f.nx = nx; f.ny = ny; f.nz = nz;
+    f.x0 = (float)geom[0]; f.y0 = (float)geom[4]; f.z0 = (float)geom[8];
+    f.idx = (float)(1.0 / geom[1]); f.idy = (float)(1.0 / geom[5]); f.idz = (float)(1.0 / geom[9]);
+    c->has_fcube = true;
+    c->has_bvec = bvec;
+    RT_CUDA(cudaStreamSynchronize(c->stream));
+    return RTGRFF_OK;
+}
+
+int rtgrff_trace(rtgrff_ctx *c, int64_t n_rays, const double *x_start, const double *y_start, const double *z_start,
+                 const double *kvec, double freq_hz, double dt, int64_t n_steps, int64_t record_stride, int trace_cs,
+                 double perturb_ratio, int s_mode, double *r_record, double *s_record, int64_t *active_steps)
+{
+    RT_TRY(use(c));
+    if (!c->has_wcube) return fail(RTGRFF_ENOCUBE, "rtgrff_set_omega_cube has not been called");
+    if (n_rays < 0 || n_steps < 0 || record_stride < 1) return fail(RTGRFF_EINVAL, "bad n_rays/n_steps/record_stride");
+    if (n_rays > 0 && (!x_start || !y_start || !z_start)) return fail(RTGRFF_EINVAL, "null start arrays");
+    const int64_t n_rec = n_steps > 0 ? (n_steps + record_stride - 1) / record_stride : 0;
+    c->rec_n = n_rec; c->rec_rays = n_rays; c->rec_has_s = trace_cs != 0;
+    if (active_steps) *active_steps = 0;
+    if (n_rays == 0 || n_rec == 0) return RTGRFF_OK;
+    const size_t nb = (size_t)n_rays * sizeof(double);
+    RT_TRY(h2d(c, c->in0, x_start, nb));
+    RT_TRY(h2d(c, c->in1, y_start, nb));
+    RT_TRY(h2d(c, c->in2, z_start, nb));
+    if (kvec) RT_TRY(h2d(c, c->in3, kvec, 3 * nb));
+    RT_TRY(c->rec_pos.reserve((size_t)n_rec * 3 * nb));
+    if (trace_cs) RT_TRY(c->rec_s.reserve((size_t)n_rec * nb));
+    RT_TRY(c->counters.reserve(64));
+    RT_CUDA(cudaMemsetAsync(c->counters.p, 0, 64, c->stream));
+
+    TraceArgs a;
+    a.cube = ray_cube_of(c);
+    a.n_rays = n_rays;
+    a.x_start = c->in0.as<double>(); a.y_start = c->in1.as<double>(); a.z_start = c->in2.as<double>();
+    a.kvec = kvec ? c->in3.as<double>() : nullptr;
+    a.omega0 = 2.0 * M_PI * freq_hz;
+    a.dt = dt; a.perturb_ratio = perturb_ratio;
+    a.n_steps = n_steps; a.stride = record_stride; a.n_rec = n_rec;
+    a.s_mode = s_mode;
+    a.rec_pos = c->rec_pos.as<double>();
+    a.rec_s = trace_cs ? c->rec_s.as<double>() : nullptr;
+    a.active_steps = c->counters.as<unsigned long long>();
+    const dim3 grid(blocks_for(n_rays, 128)), block(128);
+    const int l64 = trace_variant();
+    if (trace_cs) {
+        if (l64) trace_rays_kernel<true, true><<<grid, block, 0, c->stream>>>(a);
+        else trace_rays_kernel<true, false><<<grid, block, 0, c->stream>>>(a);
+    } else {
+        if (l64) trace_rays_kernel<false, true><<<grid, block, 0, c->stream>>>(a);
+        else trace_rays_kernel<false, false><<<grid, block, 0, c->stream>>>(a);
+    }
+    RT_TRY(launched(c, "trace_rays_kernel"));
+    if (r_record) {
+        RT_TRY(c->out0.reserve((size_t)n_rec * 3 * nb));
+        records_to_aos_kernel<<<blocks_for(n_rec * n_rays * 3, 256), 256, 0, c->stream>>>(
+            c->rec_pos.as<double>(), c->out0.as<double>(), n_rec, n_rays);
+        RT_TRY(launched(c, "records_to_aos_kernel"));
+        RT_TRY(d2h(c, r_record, c->out0.p, (size_t)n_rec * 3 * nb));
+    }
+    if (s_record && trace_cs) RT_TRY(d2h(c, s_record, c->rec_s.p, (size_t)n_rec * nb));
+    unsigned long long act = 0;
+    RT_TRY(d2h(c, &act, c->counters.p, sizeof(act)));
+    RT_CUDA(cudaStreamSynchronize(c->stream));
+    if (active_steps) *active_steps = (int64_t)act;
+    return RTGRFF_OK;
+}
+
+static int run_sampler(rtgrff_ctx *c, SampleArgs &a, double r_sun_cm, double fill_ne, double fill_te, double fill_b)
+{
+    const size_t n = (size_t)a.n_rec * a.n_rays;
+    RT_TRY(c->smp_ne.reserve(n * 4)); RT_TRY(c->smp_te.reserve(n * 4)); RT_TRY(c->smp_b.reserve(n * 4));
+    RT_TRY(c->smp_ds.reserve(n * 4)); RT_TRY(c->smp_s.reserve(n * 4)); RT_TRY(c->smp_valid.reserve(n));
+    a.fcube = c->fcube.as<float4>();
+    a.g = c->fgeomf;
+    a.r_sun_cm = (float)r_sun_cm;   // numpy 2: float32 array * python float stays float32 (gpu_raytrace.py:482-484)
+    a.fill_ne = (float)fill_ne; a.fill_te = (float)fill_te; a.fill_b = (float)fill_b;
+    a.ne = c->smp_ne.as<float>(); a.te = c->smp_te.as<float>(); a.b = c->smp_b.as<float>();
+    a.ds = c->smp_ds.as<float>(); a.s_out = c->smp_s.as<float>(); a.valid = c->smp_valid.as<uint8_t>();
+    unsigned int blocks = blocks_for((int64_t)n, 256);
+    const unsigned int cap = (unsigned int)c->sm_count * 64;
+    if (blocks > cap) blocks = cap;
+    sample_paths_kernel<<<blocks, 256, 0, c->stream>>>(a);
+    RT_TRY(launched(c, "sample_paths_kernel"));
+    c->smp_n = a.n_rec; c->smp_rays = a.n_rays;
+    return RTGRFF_OK;
+}
+
+static int sampler_out(rtgrff_ctx *c, size_t n, float *ne, float *te, float *b, float *ds, uint8_t *valid, float *s)
+{
+    if (ne) RT_TRY(d2h(c, ne, c->smp_ne.p, n * 4));
+    if (te) RT_TRY(d2h(c, te, c->smp_te.p, n * 4));
+    if (b) RT_TRY(d2h(c, b, c->smp_b.p, n * 4));
+    if (ds) RT_TRY(d2h(c, ds, c->smp_ds.p, n * 4));
+    if (valid) RT_TRY(d2h(c, valid, c->smp_valid.p, n));
+    if (s) RT_TRY(d2h(c, s, c->smp_s.p, n * 4));
+    RT_CUDA(cudaStreamSynchronize(c->stream));
+    return RTGRFF_OK;
+}
+
+int rtgrff_sample(rtgrff_ctx *c, int64_t n_rec, int64_t n_rays, const float *pos, const float *s,
+                  const float *ray_start, double r_sun_cm, double fill_ne, double fill_te, double fill_b, float *ne,
+                  float *te, float *b, float *ds, uint8_t *valid)
+{
+    RT_TRY(use(c));
+    if (!c->has_fcube) return fail(RTGRFF_ENOCUBE, "rtgrff_set_field_cubes has not been called");
+    if (n_rec < 0 || n_rays < 0) return fail(RTGRFF_EINVAL, "negative sizes");
+    const size_t n = (size_t)n_rec * n_rays;
+    if (n == 0) return RTGRFF_OK;
+    if (!pos || !s || !ray_start) return fail(RTGRFF_EINVAL, "null input");
+    RT_TRY(h2d(c, c->in0, pos, n * 3 * sizeof(float)));
+    RT_TRY(h2d(c, c->in1, s, n * sizeof(float)));
+    RT_TRY(h2d(c, c->in2, ray_start, (size_t)n_rays * 3 * sizeof(float)));
+    SampleArgs a{};
+    a.n_rec = n_rec; a.n_rays = n_rays;
+    a.pos_aos = c->in0.as<float>(); a.s32 = c->in1.as<float>(); a.ray_start = c->in2.as<float>();
+    RT_TRY(run_sampler(c, a, r_sun_cm, fill_ne, fill_te, fill_b));
+    return sampler_out(c, n, ne, te, b, ds, valid, nullptr);
+}
+
+int rtgrff_sample_traced(rtgrff_ctx *c, const float *ray_start, double r_sun_cm, double fill_ne, double fill_te,
+                         double fill_b, float *ne, float *te, float *b, float *ds, uint8_t *valid, float *s)
+{
+    RT_TRY(use(c));
+    if (!c->has_fcube) return fail(RTGRFF_ENOCUBE, "rtgrff_set_field_cubes has not been called");
+    if (c->rec_n <= 0 || c->rec_rays <= 0) return fail(RTGRFF_EINVAL, "no traced records on the device");
+    if (!ray_start) return fail(RTGRFF_EINVAL, "null ray_start");
+    const size_t n = (size_t)c->rec_n * c->rec_rays;
+    RT_TRY(h2d(c, c->in2, ray_start, (size_t)c->rec_rays * 3 * sizeof(float)));
+    SampleArgs a{};
+    a.n_rec = c->rec_n; a.n_rays = c->rec_rays;
+    a.pos_soa = c->rec_pos.as<double>();
+    a.s64 = c->rec_has_s ? c->rec_s.as<double>() : nullptr;
+    a.ray_start = c->in2.as<float>();
+    RT_TRY(run_sampler(c, a, r_sun_cm, fill_ne, fill_te, fill_b));
+    return sampler_out(c, n, ne, te, b, ds, valid, s);
+}
+
+static int run_slice(rtgrff_ctx *c, int npix, int nz, int nf, const double *rparms, const double *parms, double *rl,
+                     int32_t *status)
+{
+    const size_t pb = (size_t)15 * nz * npix * sizeof(double), rb = (size_t)3 * npix * sizeof(double);
+    const size_t ob = (size_t)7 * nf * npix * sizeof(double);
+    RT_TRY(h2d(c, c->in0, parms, pb));
+    RT_TRY(h2d(c, c->in1, rparms, rb));
+    RT_TRY(c->out0.reserve(ob));
+    RT_TRY(c->out1.reserve((size_t)npix * sizeof(int32_t)));
+    RT_CUDA(cudaMemsetAsync(c->out1.p, 0xff, (size_t)npix * sizeof(int32_t), c->stream));
+    SliceArgs a;
+    a.parms = c->in0.as<double>(); a.rparms = c->in1.as<double>();
+    a.rl = c->out0.as<double>(); a.status = c->out1.as<int32_t>();
+    a.npix = npix; a.nz = nz; a.nf = nf;
+    const int64_t warps = (int64_t)npix * nf;
+    grff_slice_kernel<<<blocks_for(warps * 32, 128), 128, 0, c->stream>>>(a);
+    RT_TRY(launched(c, "grff_slice_kernel"));
+    RT_TRY(d2h(c, rl, c->out0.p, ob));
+    if (status) RT_TRY(d2h(c, status, c->out1.p, (size_t)npix * sizeof(int32_t)));
+    RT_CUDA(cudaStreamSynchronize(c->stream));
+    return RTGRFF_OK;
+}
+
+int rtgrff_get_mw_slice(rtgrff_ctx *c, const int32_t *Lparms_M, const double *Rparms_M, const double *Parms_M,
+                        const double *T_arr, const double *DEM_arr, const double *DDM_arr, double *RL_M, int32_t *status)
+{
+    (void)T_arr; (void)DEM_arr; (void)DDM_arr;
+    RT_TRY(use(c));
+    if (!Lparms_M || !Rparms_M || !Parms_M || !RL_M) return fail(RTGRFF_EINVAL, "null argument");
+    const int npix = Lparms_M[0], nz = Lparms_M[1], nf = Lparms_M[2];
+    if (npix < 0 || nz < 0 || nf <= 0) return fail(RTGRFF_EINVAL, "bad Lparms_M {%d,%d,%d}", npix, nz, nf);
+    if (npix == 0) return RTGRFF_OK;
+    return run_slice(c, npix, nz, nf, Rparms_M, Parms_M, RL_M, status);
+}
+
+static std::mutex g_default_mu;
+static rtgrff_ctx *g_default_ctx = nullptr;
+
+int PyGET_MW(const int32_t *Lparms, const double *Rparms, const double *Parms, const double *T_arr,
+             const double *DEM_arr, const double *DDM_arr, double *RL)
+{
+    (void)T_arr; (void)DEM_arr; (void)DDM_arr;
+    if (!Lparms || !Rparms || !Parms || !RL) return 1;
+    const int nz = Lparms[0], nf = Lparms[1];
+    if (nz < 0 || nf <= 0) return 1;
+    if (Lparms[2] > 0) return 2;
+    std::lock_guard<std::mutex> lk(g_default_mu);
+    if (!g_default_ctx && rtgrff_ctx_create(0, nullptr, &g_default_ctx) != RTGRFF_OK) return 3;
+    if (use(g_default_ctx) != RTGRFF_OK) return 3;
+    return run_slice(g_default_ctx, 1, nz, nf, Rparms, Parms, RL, nullptr) == RTGRFF_OK ? 0 : 3;
+}
+
+int rtgrff_emission_traced(rtgrff_ctx *c, double pixel_area_cm2, double freq0_hz, int n_freq, double freq_log_step,
+                           int em_flag, int s_max, double *tb, double *vi)
+{
+    RT_TRY(use(c));
+    if (c->smp_n <= 0 || c->smp_rays <= 0) return fail(RTGRFF_EINVAL, "no samples on the device (call rtgrff_sample_traced)");
+    if (n_freq <= 0 || !tb || !vi) return fail(RTGRFF_EINVAL, "bad n_freq / null output");
+    const size_t n = (size_t)c->smp_rays * n_freq;
+    RT_TRY(c->out0.reserve(n * sizeof(double)));
+    RT_TRY(c->out1.reserve(n * sizeof(double)));
+    EmissionArgs a;
+    a.ne = c->smp_ne.as<float>(); a.te = c->smp_te.as<float>(); a.b = c->smp_b.as<float>(); a.ds = c->smp_ds.as<float>();
+    a.valid = c->smp_valid.as<uint8_t>();
+    a.n_rec = c->smp_n; a.n_rays = c->smp_rays;
+    a.area = pixel_area_cm2; a.freq0 = freq0_hz; a.log_step = freq_log_step;
+    a.n_freq = n_freq; a.em_flag = em_flag; a.s_max = s_max;
+    a.tb = c->out0.as<double>(); a.vi = c->out1.as<double>();
+    emission_rays_kernel<<<blocks_for((int64_t)n, 128), 128, 0, c->stream>>>(a);
+    RT_TRY(launched(c, "emission_rays_kernel"));
+    RT_TRY(d2h(c, tb, c->out0.p, n * sizeof(double)));
+    RT_TRY(d2h(c, vi, c->out1.p, n * sizeof(double)));
+    RT_CUDA(cudaStreamSynchronize(c->stream));
+    return RTGRFF_OK;
+}
+
+int rtgrff_render_map(rtgrff_ctx *c, int64_t n_rays, const double *x_start, const double *y_start,
+                      const double *z_start, const double *kvec, int n_freq, const rtgrff_freq_params *freqs,
+                      int trace_cs, double perturb_ratio, double pixel_area_cm2, double r_sun_cm, int em_flag, int s_max,
+                      int use_bvec, int voxel_order, double *tb, double *vi, int out_on_device, int64_t *stats)
+{
+    RT_TRY(use(c));
+    if (!c->has_wcube) return fail(RTGRFF_ENOCUBE, "rtgrff_set_omega_cube has not been called");
+    if (!c->has_fcube) return fail(RTGRFF_ENOCUBE, "rtgrff_set_field_cubes has not been called");
+    if (use_bvec && !c->has_bvec) return fail(RTGRFF_ENOCUBE, "use_bvec needs bx,by,bz in rtgrff_set_field_cubes");
+    if (n_rays < 0 || n_freq <= 0 || n_freq > 65535 || !freqs || !tb || !vi) return fail(RTGRFF_EINVAL, "bad arguments");
+    if (n_rays > 0 && (!x_start || !y_start || !z_start)) return fail(RTGRFF_EINVAL, "null start arrays");
+    if (stats) stats[0] = stats[1] = 0;
+    if (n_rays == 0) return RTGRFF_OK;
+    std::vector<FreqDev> fd(n_freq);
+    int64_t nominal = 0;
+    for (int f = 0; f < n_freq; ++f) {
+        if (freqs[f].n_steps < 0 || freqs[f].record_stride < 1 || !(freqs[f].freq_hz > 0.0))
+            return fail(RTGRFF_EINVAL, "bad per-frequency parameters at index %d", f);
+        fd[f].nu = freqs[f].freq_hz;
+        fd[f].omega0 = 2.0 * M_PI * freqs[f].freq_hz;
+        fd[f].dt = freqs[f].dt;
+        fd[f].n_steps = freqs[f].n_steps;
+        fd[f].stride = freqs[f].record_stride;
+        nominal += freqs[f].n_steps * n_rays;
+    }
+    const size_t nb = (size_t)n_rays * sizeof(double);
+    RT_TRY(h2d(c, c->in0, x_start, nb));
+    RT_TRY(h2d(c, c->in1, y_start, nb));
+    RT_TRY(h2d(c, c->in2, z_start, nb));
+    if (kvec) RT_TRY(h2d(c, c->in3, kvec, 3 * nb));
+    RT_TRY(c->counters.reserve(64 + (size_t)n_freq * sizeof(FreqDev)));
+    RT_CUDA(cudaMemsetAsync(c->counters.p, 0, 64, c->stream));
+    FreqDev *dfreq = reinterpret_cast<FreqDev *>(c->counters.as<char>() + 64);
+    RT_CUDA(cudaMemcpyAsync(dfreq, fd.data(), (size_t)n_freq * sizeof(FreqDev), cudaMemcpyHostToDevice, c->stream));
+    double *dtb = tb, *dvi = vi;
+    if (!out_on_device) {
+        RT_TRY(c->out0.reserve((size_t)n_freq * nb));
+        RT_TRY(c->out1.reserve((size_t)n_freq * nb));
+        dtb = c->out0.as<double>(); dvi = c->out1.as<double>();
+    }
+    MapArgs a;
+    a.cube = ray_cube_of(c);
+    a.fcube = c->fcube.as<float4>();
+    a.bcube = c->has_bvec ? c->bcube.as<float4>() : nullptr;
+    a.fg = c->fgeomf;
+    a.n_rays = n_rays;
+    a.x_start = c->in0.as<double>(); a.y_start = c->in1.as<double>(); a.z_start = c->in2.as<double>();
+    a.kvec = kvec ? c->in3.as<double>() : nullptr;
+    a.n_freq = n_freq; a.freqs = dfreq;
+    a.perturb_ratio = perturb_ratio; a.area = pixel_area_cm2;
+    a.r_sun_cm = (float)r_sun_cm; a.fill_ne = 0.0f; a.fill_te = 1e4f; a.fill_b = 0.0f;
+    a.em_flag = em_flag; a.s_max = s_max; a.use_bvec = use_bvec; a.order = voxel_order;
+    a.tb = dtb; a.vi = dvi;
+    a.active_steps = c->counters.as<unsigned long long>();
+    const dim3 grid(blocks_for(n_rays, 128), (unsigned int)n_freq), block(128);
+    const int l64 = trace_variant();
+    if (trace_cs) {
+        if (l64) render_map_kernel<true, true><<<grid, block, 0, c->stream>>>(a);
+        else render_map_kernel<true, false><<<grid, block, 0, c->stream>>>(a);
+    } else {
+        if (l64) render_map_kernel<false, true><<<grid, block, 0, c->stream>>>(a);
+        else render_map_kernel<false, false><<<grid, block, 0, c->stream>>>(a);
+    }
+    RT_TRY(launched(c, "render_map_kernel"));
+    if (!out_on_device) {
+        RT_TRY(d2h(c, tb, dtb, (size_t)n_freq * nb));
+        RT_TRY(d2h(c, vi, dvi, (size_t)n_freq * nb));
+    }
+    unsigned long long act = 0;
+    RT_TRY(d2h(c, &act, c->counters.p, sizeof(act)));
+    RT_CUDA(cudaStreamSynchronize(c->stream));
+    if (stats) { stats[0] = nominal; stats[1] = (int64_t)act; }
+    return RTGRFF_OK;
+}
+
+}  // extern "C"

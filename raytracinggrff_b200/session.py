@@ -1,0 +1,195 @@
+"""RaySession: cubes uploaded once, then any number of trace / sample / emission / render calls
+on one GPU.  The drop-in functions of gpu_raytrace.py / build_rays.py / workflow.py are thin
+wrappers over this class; every method maps 1:1 to an entry point of include/rtgrff.h."""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_double, c_float, c_int64, c_uint8
+
+import numpy as np
+
+from . import _lib
+from ._lib import FreqParams, check, f32, f64, ptr
+
+
+class RaySession:
+    def __init__(self, device=0, stream=None, context=None):
+        self.ctx = context if context is not None else _lib.Context(device, stream)
+        self._lib = _lib.load()
+        self.n_rec = 0
+        self.n_rays = 0
+        self.traced_cs = False
+
+    def close(self):
+        self.ctx.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- cubes ---------------------------------------------------------------------------------
+    def set_omega_cube(self, omega_pe_3d, x_grid, y_grid, z_grid):
+        """build_rays.py:132-143 / gpu_raytrace.py:346-357."""
+        geom = _lib.grid_geom(x_grid, y_grid, z_grid)
+        w = f64(omega_pe_3d)
+        if w.ndim != 3 or w.shape != (len(x_grid), len(y_grid), len(z_grid)):
+            raise ValueError(f"omega_pe_3d shape {w.shape} does not match the grids")
+        check(self._lib.rtgrff_set_omega_cube(self.ctx.handle, w.ctypes.data_as(ctypes.c_void_p), *w.shape,
+                                              ptr(geom, c_double), 0))
+
+    def set_field_cubes(self, x_grid, y_grid, z_grid, ne_xyz, te_xyz, b_xyz, bx=None, by=None, bz=None):
+        """gpu_raytrace.py:638-649 (_as_float32_c of each field, uniform-grid check)."""
+        geom = _lib.grid_geom(x_grid, y_grid, z_grid)
+        ne, te, b = f32(ne_xyz), f32(te_xyz), f32(b_xyz)
+        shape = (len(x_grid), len(y_grid), len(z_grid))
+        for name, a in (("ne_xyz", ne), ("te_xyz", te), ("b_xyz", b)):
+            if a.shape != shape:
+                raise ValueError(f"{name} shape {a.shape} does not match the grids {shape}")
+        vec = [None, None, None]
+        if bx is not None or by is not None or bz is not None:
+            if bx is None or by is None or bz is None:
+                raise ValueError("bx, by, bz must be given together")
+            vec = [f32(bx), f32(by), f32(bz)]
+            for a in vec:
+                if a.shape != shape:
+                    raise ValueError("B-vector cube shape does not match the grids")
+        check(self._lib.rtgrff_set_field_cubes(self.ctx.handle, ptr(ne, c_float), ptr(te, c_float), ptr(b, c_float),
+                                               ptr(vec[0], c_float), ptr(vec[1], c_float), ptr(vec[2], c_float),
+                                               *shape, ptr(geom, c_double)))
+
+    # -- integrator ----------------------------------------------------------------------------
+    def trace(self, freq_hz, x_start, y_start, z_start, kvec_in_norm, dt, n_steps, record_stride=10,
+              trace_crosssections=False, perturb_ratio=2.0, s_mode=_lib.S_PER_STEP, fetch=True):
+        """Integrate rays; returns (r_record (n_rec,n_rays,3) f64, S (n_rec,n_rays) f64 or None,
+        active_steps).  With fetch=False the records only stay on the device."""
+        xs, ys, zs = f64(x_start).ravel(), f64(y_start).ravel(), f64(z_start).ravel()
+        n_rays = xs.shape[0]
+        if ys.shape[0] != n_rays or zs.shape[0] != n_rays:
+            raise ValueError("x_start, y_start, z_start must have the same length")
+        kv = None
+        if kvec_in_norm is not None:
+            kv = f64(kvec_in_norm)
+            if kv.shape != (n_rays, 3):
+                raise ValueError(f"kvec_in_norm must have shape ({n_rays}, 3)")
+        n_steps, stride = int(n_steps), int(record_stride)
+        if stride < 1:
+            raise ValueError("record_stride must be >= 1")
+        n_rec = (n_steps + stride - 1) // stride if n_steps > 0 else 0
+        r_record = np.empty((n_rec, n_rays, 3), dtype=np.float64) if fetch else None
+        s_record = np.empty((n_rec, n_rays), dtype=np.float64) if (fetch and trace_crosssections) else None
+        active = c_int64(0)
+        check(self._lib.rtgrff_trace(self.ctx.handle, n_rays, ptr(xs, c_double), ptr(ys, c_double), ptr(zs, c_double),
+                                     ptr(kv, c_double), float(freq_hz), float(dt), n_steps, stride,
+                                     int(bool(trace_crosssections)), float(perturb_ratio), int(s_mode),
+                                     ptr(r_record, c_double), ptr(s_record, c_double), ctypes.byref(active)))
+        self.n_rec, self.n_rays, self.traced_cs = n_rec, n_rays, bool(trace_crosssections)
+        return r_record, s_record, int(active.value)
+
+    # -- sampler -------------------------------------------------------------------------------
+    def sample(self, r_record, s_arr, ray_start, r_sun_cm, fill_ne=0.0, fill_te=1e4, fill_b=0.0):
+        """gpu_raytrace.py:654-709 on host arrays; returns the reference's dict."""
+        pos = f32(np.asarray(r_record))
+        s = f32(np.asarray(s_arr))
+        rs = f32(np.asarray(ray_start))
+        if pos.ndim != 3 or pos.shape[2] != 3:
+            raise ValueError("r_record must have shape (n_steps, n_rays, 3)")
+        n_rec, n_rays, _ = pos.shape
+        if s.shape != (n_rec, n_rays):
+            raise ValueError("s_arr must have shape (n_steps, n_rays)")
+        if rs.shape != (n_rays, 3):
+            raise ValueError("ray_start must have shape (n_rays, 3)")
+        out = {k: np.empty((n_rec, n_rays), dtype=np.float32) for k in ("ne", "te", "b", "ds")}
+        valid = np.empty((n_rec, n_rays), dtype=np.uint8)
+        check(self._lib.rtgrff_sample(self.ctx.handle, n_rec, n_rays, ptr(pos, c_float), ptr(s, c_float),
+                                      ptr(rs, c_float), float(r_sun_cm), float(fill_ne), float(fill_te), float(fill_b),
+                                      ptr(out["ne"], c_float), ptr(out["te"], c_float), ptr(out["b"], c_float),
+                                      ptr(out["ds"], c_float), ptr(valid, c_uint8)))
+        out["valid_mask"] = valid.astype(bool)
+        out["s"] = s
+        return out
+
+    def sample_traced(self, ray_start, r_sun_cm, fill_ne=0.0, fill_te=1e4, fill_b=0.0, fetch=True):
+        """Sampler on the records the last trace() left on the device."""
+        rs = f32(np.asarray(ray_start))
+        if rs.shape != (self.n_rays, 3):
+            raise ValueError("ray_start must have shape (n_rays, 3)")
+        shape = (self.n_rec, self.n_rays)
+        out = {}
+        valid = None
+        if fetch:
+            out = {k: np.empty(shape, dtype=np.float32) for k in ("ne", "te", "b", "ds", "s")}
+            valid = np.empty(shape, dtype=np.uint8)
+        check(self._lib.rtgrff_sample_traced(self.ctx.handle, ptr(rs, c_float), float(r_sun_cm), float(fill_ne),
+                                             float(fill_te), float(fill_b), ptr(out.get("ne"), c_float),
+                                             ptr(out.get("te"), c_float), ptr(out.get("b"), c_float),
+                                             ptr(out.get("ds"), c_float), ptr(valid, c_uint8),
+                                             ptr(out.get("s"), c_float)))
+        if fetch:
+            out["valid_mask"] = valid.astype(bool)
+        return out
+
+    # -- GRFF ----------------------------------------------------------------------------------
+    def get_mw_slice(self, Lparms_M, Rparms_M, Parms_M, RL_M):
+        """fastGRFF get_mw_slice contract (script/resample_with_ray_tracing.py:428-446); RL_M written
+        in place (must be Fortran-ordered float64 (7,Nf,Npix)); returns status int32 (Npix)."""
+        L = np.asfortranarray(Lparms_M, dtype=np.int32)
+        R = np.asfortranarray(Rparms_M, dtype=np.float64)
+        P = np.asfortranarray(Parms_M, dtype=np.float64)
+        npix, nz, nf = int(L[0]), int(L[1]), int(L[2])
+        if P.shape != (15, nz, npix) or R.shape != (3, npix):
+            raise ValueError("Parms_M must be (15,Nz,Npix) and Rparms_M (3,Npix)")
+        if not (isinstance(RL_M, np.ndarray) and RL_M.dtype == np.float64 and RL_M.flags.f_contiguous
+                and RL_M.shape == (7, nf, npix)):
+            raise ValueError("RL_M must be a Fortran-ordered float64 array of shape (7,Nf,Npix)")
+        status = np.zeros(npix, dtype=np.int32)
+        check(self._lib.rtgrff_get_mw_slice(self.ctx.handle, ptr(L, ctypes.c_int32), ptr(R, c_double), ptr(P, c_double),
+                                            None, None, None, ptr(RL_M, c_double), ptr(status, ctypes.c_int32)))
+        return status
+
+    def emission_traced(self, pixel_area_cm2, freq0, n_freq=1, freq_log_step=0.0, em_flag=5, s_max=30):
+        """script/resample_with_ray_tracing.py:467-530 on the device samples; returns (tb, vi) each
+        (n_rays, n_freq) float64."""
+        tb = np.empty((self.n_rays, int(n_freq)), dtype=np.float64)
+        vi = np.empty_like(tb)
+        check(self._lib.rtgrff_emission_traced(self.ctx.handle, float(pixel_area_cm2), float(freq0), int(n_freq),
+                                               float(freq_log_step), int(em_flag), int(s_max), ptr(tb, c_double),
+                                               ptr(vi, c_double)))
+        return tb, vi
+
+    # -- fused map -----------------------------------------------------------------------------
+    def render_map(self, x_start, y_start, z_start, freq_params, kvec_in_norm=None, trace_crosssections=True,
+                   perturb_ratio=2.0, pixel_area_cm2=1.0, r_sun_cm=6.957e10, em_flag=5, s_max=30, use_bvec=False,
+                   voxel_order=_lib.ORDER_RECORD, out_device_ptrs=None):
+        """Fused trace+sample+transfer.  freq_params: sequence of dicts/tuples
+        (freq_hz, dt, n_steps, record_stride).  Returns (tb, vi) each (n_freq, n_rays) float64 and
+        stats {nominal_ray_steps, active_ray_steps}; with out_device_ptrs=(tb_ptr, vi_ptr) the
+        results are written to those device buffers instead and (None, None, stats) is returned."""
+        xs, ys, zs = f64(x_start).ravel(), f64(y_start).ravel(), f64(z_start).ravel()
+        n_rays = xs.shape[0]
+        kv = None
+        if kvec_in_norm is not None:
+            kv = f64(kvec_in_norm)
+            if kv.shape != (n_rays, 3):
+                raise ValueError(f"kvec_in_norm must have shape ({n_rays}, 3)")
+        nf = len(freq_params)
+        arr = (FreqParams * nf)()
+        for i, p in enumerate(freq_params):
+            if isinstance(p, dict):
+                p = (p["freq_hz"], p["dt"], p["n_steps"], p["record_stride"])
+            arr[i] = FreqParams(float(p[0]), float(p[1]), int(p[2]), int(p[3]))
+        stats = (c_int64 * 2)()
+        if out_device_ptrs is None:
+            tb = np.empty((nf, n_rays), dtype=np.float64)
+            vi = np.empty_like(tb)
+            ptb, pvi, on_dev = tb.ctypes.data_as(ctypes.c_void_p), vi.ctypes.data_as(ctypes.c_void_p), 0
+        else:
+            tb = vi = None
+            ptb, pvi, on_dev = ctypes.c_void_p(out_device_ptrs[0]), ctypes.c_void_p(out_device_ptrs[1]), 1
+        check(self._lib.rtgrff_render_map(self.ctx.handle, n_rays, ptr(xs, c_double), ptr(ys, c_double),
+                                          ptr(zs, c_double), ptr(kv, c_double), nf, arr,
+                                          int(bool(trace_crosssections)), float(perturb_ratio), float(pixel_area_cm2),
+                                          float(r_sun_cm), int(em_flag), int(s_max), int(bool(use_bvec)),
+                                          int(voxel_order), ptb, pvi, on_dev, stats))
+        return tb, vi, {"nominal_ray_steps": int(stats[0]), "active_ray_steps": int(stats[1])}

@@ -1,0 +1,190 @@
+"""Ray-traced emission map: the hot-path part of ``run_ray_tracing_emission``
+(reference: script/resample_with_ray_tracing.py:154-549) on in-memory cubes.
+
+The reference function starts from a MAS model directory and resamples it through psipy
+(:251-293) — out of scope here.  Everything after that is kept with the same
+keyword names, defaults and result keys: ray launch geometry (:295-303), tracing (:305-352),
+GRFF header (:354-365), sampling (:372-398), GRFF per pixel or batched (:400-524), scrubbing and
+the npz written at :533-540.  ``model`` is a dict with ``x_grid, y_grid, z_grid, omega_pe, ne,
+te, b`` (and optionally ``bx, by, bz``) such as ``synthetic.corona_cube`` returns.
+
+``grff_backend``:
+  'get_mw'   per-pixel ``PyGET_MW`` calls with ``Parms (15,N_valid)`` as at :467-524 (drop-in symbol)
+  'fastgrff' one batched ``get_mw_slice`` call with ``Parms_M (15,n_rec,n_rays)`` as at :400-466
+  'device'   paths and samples stay on the GPU, no Parms is materialised (rtgrff_emission_traced)
+  'fused'    single fused kernel per map (rtgrff_render_map)
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib, synthetic
+from .grff import initGET_MW
+from .session import RaySession
+
+R_sun_cm = 6.957e10      # script/resample_with_ray_tracing.py:68
+R_sun_m = 6.957e8
+c = 2.998e10             # :91
+kb = 1.38065e-16         # :92
+sfu2cgs = 1e-19          # :93
+AU_cm = 1.49599e13       # :94
+
+
+def _check_device(name, value):
+    v = value.lower()
+    if v == "cpu":
+        raise RuntimeError(f"{name}='cpu': raytracinggrff_b200 is CUDA-only (no CPU path, no fallback)")
+    if v != "cuda":
+        raise ValueError(f"Unsupported device '{value}'. Use 'cpu' or 'cuda'.")
+
+
+def pixel_area_cm2(X_fov, N_pix):
+    """script/resample_with_ray_tracing.py:360-363."""
+    pixel_size_cm = (2 * X_fov) / N_pix * R_sun_cm
+    return pixel_size_cm * pixel_size_cm
+
+
+def tb_from_rl(RL, frequencies_Hz, area):
+    """SFU -> T_b and V/I for one pixel, script/resample_with_ray_tracing.py:513-520."""
+    Nf = RL.shape[1]
+    tb = np.zeros(Nf)
+    vi = np.zeros(Nf)
+    for ifreq in range(Nf):
+        intensity_sfu = RL[5, ifreq] + RL[6, ifreq]
+        vi[ifreq] = (RL[5, ifreq] - RL[6, ifreq]) / (RL[5, ifreq] + RL[6, ifreq] + 1e-30)
+        nu_GHz = RL[0, ifreq]
+        nu_Hz = frequencies_Hz[ifreq] if nu_GHz <= 0 else nu_GHz * 1e9
+        conversion_factor = (sfu2cgs * c * c / (2.0 * kb * nu_Hz * nu_Hz) / area) * (AU_cm * AU_cm)
+        tb[ifreq] = intensity_sfu * conversion_factor
+    return tb, vi
+
+
+def pack_parms_batch(sampled, area, s_input_on=False):
+    """Parms_M (15, n_rec, n_rays) Fortran order, script/resample_with_ray_tracing.py:404-426:
+    theta=90, flag=1+4, s_max=30 everywhere; valid & finite samples compacted to the front."""
+    ne_all, te_all, b_all = sampled["ne"], sampled["te"], sampled["b"]
+    n_rec, n_rays = ne_all.shape
+    valid = sampled["valid_mask"] & np.isfinite(ne_all) & np.isfinite(te_all) & np.isfinite(b_all)
+    Parms_M = np.zeros((15, n_rec, n_rays), dtype=np.float64, order="F")
+    Parms_M[4] = 90.0
+    Parms_M[6] = 1 + 4
+    Parms_M[7] = 30
+    # stable compaction of the valid samples of every ray, vectorised over rays
+    order = np.argsort(~valid, axis=0, kind="stable")
+    cnt = valid.sum(axis=0)
+    keep = np.arange(n_rec)[:, None] < cnt[None, :]
+    for m, key in ((0, "ds"), (1, "te"), (2, "ne"), (3, "b")):
+        Parms_M[m] = np.where(keep, np.take_along_axis(sampled[key].astype(np.float64), order, axis=0), 0.0)
+    if s_input_on:
+        Parms_M[14] = np.where(keep, np.take_along_axis(sampled["s"].astype(np.float64), order, axis=0) * area, 0.0)
+    return Parms_M
+
+
+def run_ray_tracing_emission(model, N_pix=64, X_fov=1.44, freq_hz=75e6, z_observer=3.0, dt=6e-3, n_steps=5000,
+                             record_stride=10, n_workers=1, s_input_on=False, out_path=None, grff_lib=None, Nfreq=1,
+                             freq0=None, freq_log_step=0.0, save_plots=False, verbose=True, device="cuda",
+                             fallback_to_cpu=False, raytrace_device="cuda", grff_backend="get_mw",
+                             perturb_ratio=2, session=None, return_samples=False):
+    if freq0 is None:
+        freq0 = freq_hz
+    backend = grff_backend.lower()
+    if backend not in ("get_mw", "fastgrff", "device", "fused"):
+        raise ValueError(f"Unsupported grff_backend '{grff_backend}'. Use 'get_mw', 'fastgrff', 'device' or 'fused'.")
+    _check_device("device", device)
+    _check_device("raytrace_device", raytrace_device)
+    if s_input_on:
+        raise NotImplementedError("s_input_on relies on a private GRFF build (Parms[14] = S*area is a reserved "
+                                  "slot upstream); its semantics are not defined by the reference")
+    ses = session or RaySession(context=_lib.default_context(0))
+    xg, yg, zg = model["x_grid"], model["y_grid"], model["z_grid"]
+    ses.set_omega_cube(model["omega_pe"], xg, yg, zg)
+    ses.set_field_cubes(xg, yg, zg, model["ne"], model["te"], model["b"])
+
+    x_flat, y_flat, z_start, kvec = synthetic.ray_launch_geometry(N_pix, X_fov, z_observer)
+    n_rays = len(x_flat)
+    Nf = int(Nfreq)
+    frequencies_Hz = synthetic.log_frequencies(freq0, Nf, freq_log_step)
+    area = pixel_area_cm2(X_fov, N_pix)
+    x_coords = np.linspace(-X_fov, X_fov, N_pix) * R_sun_m
+    y_coords = np.linspace(-X_fov, X_fov, N_pix) * R_sun_m
+    emission_cube = np.zeros((N_pix, N_pix, Nf), dtype="double")
+    emission_polVI_cube = np.zeros((N_pix, N_pix, Nf), dtype="double")
+    ray_start = np.column_stack([x_flat, y_flat, z_start])
+    sampled = None
+
+    if backend == "fused":
+        if Nf != 1 or abs(freq0 - freq_hz) > 0:
+            raise ValueError("the fused backend traces and emits at the same frequency: use Nfreq=1, freq0=freq_hz "
+                             "(or RaySession.render_map for a list of frequencies)")
+        tb, vi, _ = ses.render_map(x_flat, y_flat, z_start, [(freq_hz, dt, n_steps, record_stride)],
+                                   kvec_in_norm=kvec, trace_crosssections=True, perturb_ratio=perturb_ratio,
+                                   pixel_area_cm2=area, r_sun_cm=R_sun_cm)
+        emission_cube[:, :, 0] = tb[0].reshape(N_pix, N_pix)
+        emission_polVI_cube[:, :, 0] = vi[0].reshape(N_pix, N_pix)
+    else:
+        keep_host = backend in ("get_mw", "fastgrff") or return_samples
+        ses.trace(freq_hz, x_flat, y_flat, z_start, kvec, dt, n_steps, record_stride, True, perturb_ratio,
+                  fetch=False)
+        sampled = ses.sample_traced(ray_start, R_sun_cm, 0.0, 1e4, 0.0, fetch=keep_host)
+        if backend == "device":
+            tb, vi = ses.emission_traced(area, freq0, Nf, freq_log_step)
+            emission_cube[:] = tb.reshape(N_pix, N_pix, Nf)
+            emission_polVI_cube[:] = vi.reshape(N_pix, N_pix, Nf)
+        elif backend == "fastgrff":
+            n_rec = sampled["ne"].shape[0]
+            Parms_M = pack_parms_batch(sampled, area, s_input_on)
+            Lparms_M = np.array([n_rays, n_rec, Nf, 1, 0, 0], dtype=np.int32)
+            Rparms_M = np.zeros((3, n_rays), dtype=np.float64, order="F")
+            Rparms_M[0, :], Rparms_M[1, :], Rparms_M[2, :] = area, freq0, freq_log_step
+            RL_M = np.zeros((7, Nf, n_rays), dtype=np.float64, order="F")
+            status = ses.get_mw_slice(Lparms_M, Rparms_M, Parms_M, RL_M)
+            if np.any(status != 0) and verbose:
+                print(f"get_mw_slice: warning {np.count_nonzero(status)} pixels returned non-zero status")
+            for p in range(n_rays):
+                if status[p] != 0:
+                    continue
+                tb, vi = tb_from_rl(RL_M[:, :, p], frequencies_Hz, area)
+                emission_cube[p // N_pix, p % N_pix] = tb
+                emission_polVI_cube[p // N_pix, p % N_pix] = vi
+        else:  # 'get_mw': the reference's per-pixel loop, script/resample_with_ray_tracing.py:467-524
+            GET_MW = initGET_MW(grff_lib)
+            Lparms = np.zeros(5, dtype="int32")
+            Lparms[1] = Nf
+            Rparms = np.array([area, freq0, freq_log_step], dtype="double")
+            dummy = np.array(0, dtype="double")
+            for p in range(n_rays):
+                valid = (sampled["valid_mask"][:, p] & np.isfinite(sampled["ne"][:, p])
+                         & np.isfinite(sampled["te"][:, p]) & np.isfinite(sampled["b"][:, p]))
+                if not np.any(valid):
+                    continue
+                n_valid = int(np.count_nonzero(valid))
+                Parms = np.zeros((15, n_valid), dtype="double", order="F")
+                Parms[0] = sampled["ds"][:, p][valid]
+                Parms[1] = sampled["te"][:, p][valid]
+                Parms[2] = sampled["ne"][:, p][valid]
+                Parms[3] = sampled["b"][:, p][valid]
+                Parms[4] = 90.0
+                Parms[6] = 1 + 4
+                Parms[7] = 30
+                L = Lparms.copy()
+                L[0] = n_valid
+                RL = np.zeros((7, Nf), dtype="double", order="F")
+                if GET_MW(L, Rparms, Parms, dummy, dummy, dummy, RL) != 0:
+                    continue
+                tb, vi = tb_from_rl(RL, frequencies_Hz, area)
+                emission_cube[p // N_pix, p % N_pix] = tb
+                emission_polVI_cube[p // N_pix, p % N_pix] = vi
+
+    emission_cube = np.nan_to_num(emission_cube, nan=0.0, posinf=0.0, neginf=0.0)
+    result = {
+        "emission_cube": emission_cube,
+        "emission_polVI_cube": emission_polVI_cube,
+        "frequencies_Hz": frequencies_Hz,
+        "x_coords": x_coords,
+        "y_coords": y_coords,
+    }
+    if out_path is not None:
+        np.savez_compressed(out_path, **result)
+    if return_samples and sampled:
+        result["sampled"] = sampled
+    return result

@@ -1,0 +1,331 @@
+"""GPU parity tests (run on the B200 box: ``pytest -m gpu``).  Everything goes through the C ABI
+of librtgrff_b200.so via the drop-in Python API and is compared with the CPU oracle on the same
+seeded inputs and with the golden vectors produced by the unmodified reference.
+
+Tolerances (BASELINE.json north_star):
+  ray endpoints / path samples   <= 1e-5 R_sun absolute
+  cross-section ratio S          <= 1e-4 relative
+  sampler ne/te/b                bit-exact (reference GPU-vs-CPU tolerance is 1e-5), ds 1e-6 relative
+  T_b, Stokes I, V               <= 1e-4 relative
+"""
+import numpy as np
+import pytest
+
+import cases
+import grff_checks
+from raytracinggrff_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+POS_TOL = 1e-5
+S_RTOL = 1e-4
+TB_RTOL = 1e-4
+
+
+def _cmp_paths(r, s, r_ref, s_ref, ext_hi=None):
+    assert r.shape == r_ref.shape and r.dtype == np.float64
+    nan_a, nan_b = np.isnan(r), np.isnan(r_ref)
+    assert np.array_equal(nan_a, nan_b)
+    d = np.abs(np.nan_to_num(r) - np.nan_to_num(r_ref))
+    assert d.max() <= POS_TOL, f"max |dr| = {d.max():.3e} R_sun"
+    if s_ref is not None:
+        assert np.array_equal(np.isnan(s), np.isnan(s_ref))
+        ok = np.isfinite(s_ref)
+        rel = np.abs(s[ok] - s_ref[ok]) / np.abs(s_ref[ok])
+        assert rel.max() <= S_RTOL, f"max rel dS = {rel.max():.3e}"
+    return d.max()
+
+
+# ------------------------------------------------------------------------------ integrator ----
+@pytest.mark.parametrize("name", cases.TRACE_CASES)
+def test_trace_ray_matches_reference_golden(golden, name):
+    from raytracinggrff_b200 import trace_ray
+    kw = cases.trace_case(name)
+    g = golden(f"trace_{name}")
+    r, cs = trace_ray("cuda", **kw)
+    s_ref = g["s_record"] if kw["trace_crosssections"] else None
+    s = np.array(cs) if kw["trace_crosssections"] else None
+    if not kw["trace_crosssections"]:
+        assert cs == []
+    _cmp_paths(r, s, g["r_record"], s_ref)
+
+
+def test_ray_trace_full_config3_matches_oracle(oracle):
+    """BASELINE config 3 at full size (64^2 rays, 128^3 cube, 5000 steps) against the oracle."""
+    from raytracinggrff_b200 import ray_trace
+    c = synthetic.corona_cube(128, 3.0)
+    xs, ys, zs, kv = synthetic.ray_launch_geometry(64, 1.44, 3.0)
+    kw = dict(omega_pe_3d=c["omega_pe"], x_grid=c["x_grid"], y_grid=c["y_grid"], z_grid=c["z_grid"], freq_hz=75e6,
+              x_start=xs, y_start=ys, z_start=zs, kvec_in_norm=kv, dt=6e-3, n_steps=5000, record_stride=10,
+              trace_crosssections=True, perturb_ratio=2)
+    r_ref, cs_ref = oracle.ray_trace(**kw)
+    r, cs = ray_trace(**kw)
+    assert isinstance(cs, list) and len(cs) == 500 and cs[0].shape == (4096,)
+    _cmp_paths(r, np.array(cs), r_ref, np.array(cs_ref))
+
+
+def test_trace_edge_cases(oracle, session):
+    g = np.linspace(-1.0, 1.0, 9)
+    w = np.full((9, 9, 9), 2e8)
+    session.set_omega_cube(w, g, g, g)
+    # zero rays / zero steps
+    r, s, act = session.trace(80e6, np.zeros(0), np.zeros(0), np.zeros(0), np.zeros((0, 3)), 1e-2, 10, 3, True)
+    assert r.shape == (4, 0, 3) and s.shape == (4, 0) and act == 0
+    r, s, act = session.trace(80e6, np.zeros(2), np.zeros(2), np.zeros(2), None, 1e-2, 0, 3, False)
+    assert r.shape == (0, 2, 3) and s is None
+    # evanescent start (omega < omega_pe => kc0 = 0 => omega > 0 but k = 0: ray is pushed by grad only = 0 here)
+    xs = np.array([0.0, 0.3]); ys = np.array([0.0, -0.2]); zs = np.array([0.5, 0.9])
+    kv = np.array([[0, 0, -1.0], [0, 0, -1.0]])
+    r, s, _ = session.trace(10e6, xs, ys, zs, kv, 1e-2, 20, 1, True)
+    r_ref, cs_ref = oracle.ray_trace(w, g, g, g, 10e6, xs, ys, zs, kv, 1e-2, 20, 1, True)
+    _cmp_paths(r, s, r_ref, np.array(cs_ref))
+    # NaN start position and start outside the cube: NaN k, frozen, S NaN
+    xs = np.array([np.nan, 1.5, 0.0])
+    r, s, act = session.trace(300e6, xs, np.zeros(3), np.zeros(3), np.tile([[0, 0, -1.0]], (3, 1)), 1e-2, 30, 7, True)
+    r_ref, cs_ref = oracle.ray_trace(w, g, g, g, 300e6, xs, np.zeros(3), np.zeros(3), np.tile([[0, 0, -1.0]], (3, 1)),
+                                     1e-2, 30, 7, True)
+    _cmp_paths(r, s, r_ref, np.array(cs_ref))
+    assert np.all(np.isnan(s[:, :2]))
+    # cumulative S = running product of the per-step ratios
+    c = synthetic.corona_cube(32, 3.0)
+    session.set_omega_cube(c["omega_pe"], c["x_grid"], c["y_grid"], c["z_grid"])
+    xs, ys, zs, kv = synthetic.ray_launch_geometry(4, 1.0, 3.0)
+    _, s_step, _ = session.trace(75e6, xs, ys, zs, kv, 6e-3, 200, 1, True, 2.0, s_mode=0)
+    _, s_cum, _ = session.trace(75e6, xs, ys, zs, kv, 6e-3, 200, 1, True, 2.0, s_mode=1)
+    np.testing.assert_allclose(s_cum, np.cumprod(s_step, axis=0), rtol=1e-12)
+
+
+def test_trace_invariants_at_scale(session):
+    """Size-independent properties on a config-4-sized launch (512^2 rays, 256^3 cube):
+    vacuum rays are straight with |dr/dt| = C_R, S = 1; the image-plane mirror symmetry of the
+    corona (x -> -x) maps ray p to its mirror ray."""
+    from raytracinggrff_b200 import C_R
+    n = 256
+    g = np.linspace(-3.0, 3.0, n)
+    session.set_omega_cube(np.zeros((n, n, n)), g, g, g)
+    xs, ys, zs, kv = synthetic.ray_launch_geometry(512, 1.44, 3.0)
+    dt, steps, stride = 6e-3, 600, 100
+    r, s, act = session.trace(75e6, xs, ys, zs, kv, dt, steps, stride, True, 2.0)
+    t = dt * (np.arange(0, steps, stride) + 1)
+    expect_z = zs[None, :] - C_R * t[:, None]
+    assert np.abs(r[..., 2] - expect_z).max() < 1e-11
+    assert np.abs(r[..., 0] - xs[None]).max() == 0 and np.abs(r[..., 1] - ys[None]).max() == 0
+    assert np.abs(s - 1.0).max() < 1e-8
+    assert act == steps * xs.size
+    c = synthetic.corona_cube(n, 3.0)
+    session.set_omega_cube(c["omega_pe"], c["x_grid"], c["y_grid"], c["z_grid"])
+    r, s, act = session.trace(75e6, xs, ys, zs, kv, dt, 3000, 300, False)
+    img = r.reshape(r.shape[0], 512, 512, 3)
+    mirror = img[:, :, ::-1, :] * np.array([-1.0, 1.0, 1.0])
+    assert np.nanmax(np.abs(img - mirror)) < 1e-6
+    assert 0 < act < 3000 * xs.size
+
+
+# --------------------------------------------------------------------------------- sampler ----
+@pytest.mark.parametrize("seed", (1, 2, 3))
+def test_sampler_matches_reference_fixture(oracle, golden, seed):
+    """The reference's GPU-vs-CPU test (tests/test_gpu_raytrace.py:91-110) with its tolerances, plus
+    bit-exactness against the reference CPU output."""
+    from raytracinggrff_b200 import sample_model_with_rays
+    args = cases.sampler_fixture(seed)
+    gpu = sample_model_with_rays("cuda", *args, r_sun_cm=1.0)
+    cpu = golden(f"sampler_fixture_seed{seed}")
+    assert np.array_equal(cpu["valid_mask"], gpu["valid_mask"])
+    assert gpu["valid_mask"].dtype == bool
+    np.testing.assert_allclose(cpu["ne"], gpu["ne"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(cpu["te"], gpu["te"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(cpu["b"], gpu["b"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(cpu["ds"], gpu["ds"], rtol=1e-6, atol=1e-6)
+    for k in ("ne", "te", "b", "ds", "s"):
+        assert gpu[k].dtype == np.float32
+        assert np.array_equal(cpu[k], gpu[k], equal_nan=True), k
+    orc = oracle.sample_model_with_rays_cpu(*args, r_sun_cm=1.0)
+    for k in ("ne", "te", "b", "ds", "valid_mask"):
+        assert np.array_equal(orc[k], gpu[k], equal_nan=True), k
+
+
+def test_sampler_config1_full_size(oracle):
+    """BASELINE config 1 at full size: 65 536 rays x 256 samples, 128^3 cube."""
+    from raytracinggrff_b200 import sample_model_with_rays
+    args = synthetic.los_sampler_case(256, 256, 128, seed=0)
+    gpu = sample_model_with_rays("cuda", *args, r_sun_cm=6.957e10)
+    cpu = oracle.sample_model_with_rays_cpu(*args, r_sun_cm=6.957e10)
+    for k in ("ne", "te", "b", "valid_mask"):
+        assert np.array_equal(cpu[k], gpu[k], equal_nan=True), k
+    np.testing.assert_allclose(cpu["ds"], gpu["ds"], rtol=1e-6, atol=0)
+
+
+def test_sampler_edge_cases(oracle, session):
+    xg, yg, zg, ne, te, b, r_record, s_arr, ray_start = cases.sampler_fixture(5)
+    session.set_field_cubes(xg, yg, zg, ne, te, b)
+    # empty inputs
+    out = session.sample(np.zeros((0, 4, 3)), np.zeros((0, 4)), np.zeros((4, 3)), 1.0)
+    assert out["ne"].shape == (0, 4)
+    # all-invalid rays, NaN / inf positions, points exactly on the faces, ragged validity
+    r = r_record.copy(); s = s_arr.copy()
+    s[:, 0] = 0.0
+    s[:, 1] = -1.0
+    r[3, 2, 1] = np.nan
+    r[4, 3, 2] = np.inf
+    r[5, 4] = [1.0, -1.0, 1.0]
+    r[6, 5] = [1.0000001, 0.0, 0.0]
+    s[::2, 6] = np.nan
+    s[:-1, 7] = 0.0
+    gpu = session.sample(r, s, ray_start, 6.957e10, fill_ne=-1.0, fill_te=123.0, fill_b=7.0)
+    cpu = oracle.sample_model_with_rays_cpu(xg, yg, zg, ne, te, b, r, s, ray_start, 6.957e10, -1.0, 123.0, 7.0)
+    for k in ("ne", "te", "b", "valid_mask"):
+        assert np.array_equal(cpu[k], gpu[k], equal_nan=True), k
+    np.testing.assert_allclose(cpu["ds"], gpu["ds"], rtol=1e-6, atol=0)
+    assert not gpu["valid_mask"][:, :2].any() and np.all(gpu["ds"][:, :2] == 0)
+    # float64 r_record straight from the integrator (cast to float32 like _as_float32_c)
+    gpu64 = session.sample(r.astype(np.float64), s.astype(np.float64), ray_start.astype(np.float64), 6.957e10,
+                           -1.0, 123.0, 7.0)
+    for k in ("ne", "te", "b", "ds", "valid_mask"):
+        assert np.array_equal(gpu64[k], gpu[k], equal_nan=True), k
+    with pytest.raises(ValueError):
+        session.sample(r[:, :, :2], s, ray_start, 1.0)
+
+
+def test_sample_traced_equals_host_round_trip(oracle, golden, session):
+    kw = cases.trace_case("corona_cs")
+    c = synthetic.corona_cube(48, 3.0)
+    session.set_omega_cube(c["omega_pe"], c["x_grid"], c["y_grid"], c["z_grid"])
+    session.set_field_cubes(c["x_grid"], c["y_grid"], c["z_grid"], c["ne"], c["te"], c["b"])
+    r, s, _ = session.trace(kw["freq_hz"], kw["x_start"], kw["y_start"], kw["z_start"], kw["kvec_in_norm"], kw["dt"],
+                            kw["n_steps"], kw["record_stride"], True, 2.0)
+    ray_start = np.column_stack([kw["x_start"], kw["y_start"], kw["z_start"]])
+    dev = session.sample_traced(ray_start, 6.957e10)
+    host = session.sample(r, s, ray_start, 6.957e10)
+    for k in ("ne", "te", "b", "ds", "valid_mask", "s"):
+        assert np.array_equal(dev[k], host[k], equal_nan=True), k
+    # and against the oracle fed the oracle's own paths (differences only through |dr| <= 1e-5)
+    g = golden("sampler_on_traced_paths")
+    assert np.mean(dev["valid_mask"] == g["valid_mask"]) > 0.999
+    both = dev["valid_mask"] & g["valid_mask"]
+    np.testing.assert_allclose(dev["ne"][both], g["ne"][both], rtol=2e-3)
+
+
+# ------------------------------------------------------------------------------------ GRFF ----
+@pytest.mark.parametrize("check", grff_checks.ALL_CHECKS, ids=lambda f: f.__name__)
+def test_pyget_mw_analytic(check):
+    """The drop-in PyGET_MW symbol bound exactly as the reference binds GRFF's
+    (script/resample_with_ray_tracing.py:79-86)."""
+    from raytracinggrff_b200 import initGET_MW
+    check(initGET_MW())
+
+
+@pytest.mark.parametrize("cfg", [dict(theta90=True, flag=5, with_b=True), dict(theta90=False, flag=4, with_b=True),
+                                 dict(theta90=True, flag=5, with_b=False), dict(theta90=False, flag=0, with_b=True)],
+                         ids=["ff_theta90", "grff_theta_var", "ff_noB", "all_on"])
+def test_get_mw_slice_matches_oracle(oracle, session, cfg):
+    rng = np.random.default_rng(11)
+    npix, nz, nf = 257, 77, 4
+    P = grff_checks.random_los_batch(rng, npix, nz, **cfg)
+    L = np.array([npix, nz, nf, 1, 0, 0], dtype=np.int32)
+    R = np.zeros((3, npix), order="F")
+    R[0], R[1], R[2] = 2.5e17, 2e8, 0.25
+    RL_ref = np.zeros((7, nf, npix), order="F")
+    oracle.get_mw_slice(L, R, P, None, None, None, RL_ref)
+    RL = np.zeros((7, nf, npix), order="F")
+    status = session.get_mw_slice(L, R, P, RL)
+    assert np.all(status == 0)
+    np.testing.assert_allclose(RL[0], RL_ref[0], rtol=1e-14)
+    scale = np.abs(RL_ref[1:]).max(axis=0, keepdims=True) + 1e-300
+    assert (np.abs(RL[1:] - RL_ref[1:]) / scale).max() <= TB_RTOL
+    np.testing.assert_allclose(RL[1:], RL_ref[1:], rtol=TB_RTOL, atol=1e-12 * float(scale.max()))
+
+
+def test_get_mw_slice_config2_shape(oracle, session):
+    """BASELINE config 2 shape at reduced pixel count: straight LOS, 400 irregular z samples,
+    free-free, 4 frequencies from 450 MHz, packed exactly as synthetic_FF_map does (:168-224)."""
+    from raytracinggrff_b200 import get_mw_slice
+    los = synthetic.straight_los_case(N_pix=48, N_z=400)
+    npix, nz, nf = 48 * 48, 400, 4
+    ne, te, b, ds = (los[k].reshape(npix, nz) for k in ("Ne_LOS", "Te_LOS", "B_LOS", "ds_LOS"))
+    valid = ~(np.isnan(ne) | np.isnan(te) | np.isnan(b))
+    P = np.zeros((15, nz, npix), order="F")
+    P[4], P[6], P[7] = 90.0, 5, 30
+    order = np.argsort(~valid, axis=1, kind="stable")
+    keep = np.arange(nz)[None, :] < valid.sum(axis=1)[:, None]
+    for m, a in ((0, ds), (1, te), (2, ne), (3, b)):
+        P[m] = np.where(keep, np.take_along_axis(a, order, axis=1), 0.0).T
+    area = (los["x_coords"][1] - los["x_coords"][0]) ** 2 * 1e4
+    L = np.array([npix, nz, nf, 1, 0, 0], dtype=np.int32)
+    R = np.zeros((3, npix), order="F")
+    R[0], R[1], R[2] = area, 450e6, 0.1
+    RL_ref = np.zeros((7, nf, npix), order="F")
+    oracle.get_mw_slice(L, R, P, None, None, None, RL_ref)
+    RL = np.zeros((7, nf, npix), order="F")
+    status = get_mw_slice(L, R, P, 0, 0, 0, RL, tile_pixels=256, heap_bytes=2 << 30)
+    assert np.all(status == 0)
+    np.testing.assert_allclose(RL[5:], RL_ref[5:], rtol=TB_RTOL, atol=1e-9 * RL_ref[5:].max())
+    tb = (RL[5] + RL[6]) * 1e-19 * 2.998e10 ** 2 / (2 * 1.38065e-16 * (RL[0] * 1e9) ** 2) / area * 1.49599e13 ** 2
+    assert 5e4 < np.median(tb[0][tb[0] > 0]) < 2.5e6     # quiet-Sun brightness temperatures at 450 MHz
+
+
+# ---------------------------------------------------------------------- pipeline / fused map ----
+def _oracle_chain(oracle, c, N_pix, X_fov, z_obs, freq, dt, n_steps, stride):
+    xs, ys, zs, kv = synthetic.ray_launch_geometry(N_pix, X_fov, z_obs)
+    r, cs = oracle.ray_trace(c["omega_pe"], c["x_grid"], c["y_grid"], c["z_grid"], freq, xs, ys, zs, kv, dt, n_steps,
+                             stride, True, perturb_ratio=2)
+    smp = oracle.sample_model_with_rays_cpu(c["x_grid"], c["y_grid"], c["z_grid"], c["ne"], c["te"], c["b"], r,
+                                            np.array(cs), np.column_stack([xs, ys, zs]), 6.957e10)
+    return oracle.emission_from_samples(smp, N_pix, X_fov, freq)
+
+
+def _cmp_maps(tb, vi, tb_ref, vi_ref):
+    assert tb.shape == tb_ref.shape
+    assert np.array_equal(tb_ref == 0, tb == 0)
+    nz = tb_ref != 0
+    rel = np.abs(tb[nz] - tb_ref[nz]) / np.abs(tb_ref[nz])
+    assert rel.max() <= TB_RTOL, f"max rel dT_b = {rel.max():.3e}"
+    assert np.abs(vi - vi_ref).max() <= TB_RTOL, f"max |d(V/I)| = {np.abs(vi - vi_ref).max():.3e}"
+
+
+@pytest.mark.parametrize("backend", ["get_mw", "fastgrff", "device", "fused"])
+def test_run_ray_tracing_emission_matches_oracle_chain(oracle, backend):
+    """The workflow of script/resample_with_ray_tracing.py:295-530 (config-3 physics, 16^2 pixels,
+    64^3 cube) through each GRFF backend against oracle trace -> oracle sampler -> oracle GET_MW."""
+    from raytracinggrff_b200.workflow import run_ray_tracing_emission
+    c = synthetic.corona_cube(64, 3.0)
+    args = dict(N_pix=16, X_fov=1.44, freq_hz=75e6, z_observer=3.0, dt=6e-3, n_steps=5000, record_stride=10)
+    tb_ref, vi_ref, f_ref = _oracle_chain(oracle, c, 16, 1.44, 3.0, 75e6, 6e-3, 5000, 10)
+    res = run_ray_tracing_emission(c, **args, grff_backend=backend, device="cuda", raytrace_device="cuda",
+                                   verbose=False)
+    assert set(res) >= {"emission_cube", "emission_polVI_cube", "frequencies_Hz", "x_coords", "y_coords"}
+    np.testing.assert_array_equal(res["frequencies_Hz"], f_ref)
+    assert res["emission_cube"].shape == (16, 16, 1)
+    assert (tb_ref > 1e4).mean() > 0.5
+    _cmp_maps(res["emission_cube"], res["emission_polVI_cube"], tb_ref, vi_ref)
+
+
+def test_render_map_multi_frequency_and_orders(oracle, session):
+    """Fused map at three frequencies with per-frequency presets; record order (reference behaviour)
+    and reversed order (far end first) against the oracle fed the same / reversed voxel lists;
+    theta from the B vector against a numpy restatement of the angle."""
+    c = synthetic.corona_cube(64, 3.0, active_region=True)
+    session.set_omega_cube(c["omega_pe"], c["x_grid"], c["y_grid"], c["z_grid"])
+    session.set_field_cubes(c["x_grid"], c["y_grid"], c["z_grid"], c["ne"], c["te"], c["b"], c["bx"], c["by"], c["bz"])
+    N_pix, X_fov = 12, 1.2
+    xs, ys, zs, kv = synthetic.ray_launch_geometry(N_pix, X_fov, 3.0)
+    area = (2 * X_fov / N_pix * 6.957e10) ** 2
+    freqs = [75e6, 150e6, 400e6]
+    fps = [dict(freq_hz=f, **synthetic.frequency_scaled_params(f)) for f in freqs]
+    tb, vi, stats = session.render_map(xs, ys, zs, fps, kvec_in_norm=kv, pixel_area_cm2=area)
+    assert tb.shape == (3, N_pix * N_pix)
+    assert stats["nominal_ray_steps"] == sum(p["n_steps"] for p in fps) * xs.size
+    assert 0 < stats["active_ray_steps"] <= stats["nominal_ray_steps"]
+    for i, p in enumerate(fps):
+        tb_ref, vi_ref, _ = _oracle_chain(oracle, c, N_pix, X_fov, 3.0, p["freq_hz"], p["dt"], p["n_steps"],
+                                          p["record_stride"])
+        _cmp_maps(tb[i].reshape(N_pix, N_pix, 1), vi[i].reshape(N_pix, N_pix, 1), tb_ref, vi_ref)
+    # reversed voxel order == oracle GET_MW on the reversed compacted list
+    p = fps[1]
+    tb_r, vi_r, _ = session.render_map(xs, ys, zs, [p], kvec_in_norm=kv, pixel_area_cm2=area, voxel_order=1)
+    r, cs = oracle.ray_trace(c["omega_pe"], c["x_grid"], c["y_grid"], c["z_grid"], p["freq_hz"], xs, ys, zs, kv,
+                             p["dt"], p["n_steps"], p["record_stride"], True, perturb_ratio=2)
+    smp = oracle.sample_model_with_rays_cpu(c["x_grid"], c["y_grid"], c["z_grid"], c["ne"], c["te"], c["b"], r,
+                                            np.array(cs), np.column_stack([xs, ys, zs]), 6.957e10)
+    rev = {k: v[::-1].copy() for k, v in smp.items()}
+    tb_ref, vi_ref, _ = oracle.emission_from_samples(rev, N_pix, X_fov, p["freq_hz"])
+    _cmp_maps(tb_r[0].reshape(N_pix, N_pix, 1), vi_r[0].reshape(N_pix, N_pix, 1), tb_ref, vi_ref)
