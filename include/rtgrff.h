@@ -44,6 +44,9 @@ int rtgrff_ctx_destroy(rtgrff_ctx *ctx);
 int rtgrff_ctx_synchronize(rtgrff_ctx *ctx);
 /* Kernel launches issued by this context since creation (for bench.py's gpu_launches). */
 int64_t rtgrff_ctx_launch_count(const rtgrff_ctx *ctx);
+/* Device time in ms of the dominant kernel of the last trace/sample/get_mw_slice/emission/render
+ * call, measured with CUDA events on the context's stream (-1 if none).  Synchronises on the event. */
+double rtgrff_ctx_last_kernel_ms(rtgrff_ctx *ctx);
 
 /*
  * Grid geometry of one axis: {g[0], mean step, g[n-1], g[1]-g[0]}: (g0, step) exactly as the

@@ -30,7 +30,7 @@ ORDER_REVERSED = 1
 # every symbol include/rtgrff.h declares (tests check the library exports all of them)
 EXPORTS = (
     "rtgrff_version", "rtgrff_last_error", "rtgrff_device_count", "rtgrff_ctx_create", "rtgrff_ctx_destroy",
-    "rtgrff_ctx_synchronize", "rtgrff_ctx_launch_count", "rtgrff_set_omega_cube", "rtgrff_set_field_cubes",
+    "rtgrff_ctx_synchronize", "rtgrff_ctx_launch_count", "rtgrff_ctx_last_kernel_ms", "rtgrff_set_omega_cube", "rtgrff_set_field_cubes",
     "rtgrff_trace", "rtgrff_sample", "rtgrff_sample_traced", "PyGET_MW", "rtgrff_get_mw_slice",
     "rtgrff_emission_traced", "rtgrff_render_map",
 )
@@ -63,6 +63,8 @@ def load():
     lib.rtgrff_ctx_synchronize.argtypes = [c_void_p]
     lib.rtgrff_ctx_launch_count.argtypes = [c_void_p]
     lib.rtgrff_ctx_launch_count.restype = c_int64
+    lib.rtgrff_ctx_last_kernel_ms.argtypes = [c_void_p]
+    lib.rtgrff_ctx_last_kernel_ms.restype = c_double
     lib.rtgrff_set_omega_cube.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, dp, c_int]
     lib.rtgrff_set_field_cubes.argtypes = [c_void_p, fp, fp, fp, fp, fp, fp, c_int, c_int, c_int, dp]
     lib.rtgrff_trace.argtypes = [c_void_p, c_int64, dp, dp, dp, dp, c_double, c_double, c_int64, c_int64, c_int,
@@ -180,6 +182,10 @@ class Context:
     @property
     def launch_count(self):
         return int(self._lib.rtgrff_ctx_launch_count(self.handle))
+
+    @property
+    def last_kernel_ms(self):
+        return float(self._lib.rtgrff_ctx_last_kernel_ms(self.handle))
 
     def synchronize(self):
         check(self._lib.rtgrff_ctx_synchronize(self.handle))

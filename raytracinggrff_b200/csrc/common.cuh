@@ -74,6 +74,8 @@ struct rtgrff_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int64_t launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // bracket the dominant kernel of the last call
+    bool ev_valid = false;
 
     // ray cube {omega_pe, d/dx, d/dy, d/dz}
     rtgrff::DevBuf wcube;

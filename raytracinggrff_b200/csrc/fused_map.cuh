@@ -15,6 +15,8 @@
 #include "los_sampler.cuh"
 #include "ray_integrator.cuh"
 
+#include <type_traits>
+
 namespace rtgrff {
 
 struct FreqDev {
@@ -78,9 +80,52 @@ struct OutwardTransfer {
     }
 };
 
-template <bool CS, bool LERP64>
+// NEED_BETWEEN: gyroresonance on or theta from the B vector -> the previous voxel must be kept for
+// the between-voxel events; with the reference's packing (theta = 90, GR off) it is dead weight.
+template <bool NEED_BETWEEN>
+struct RecordTransfer {
+    PolState<1> st;
+    Voxel prev;
+    bool have_prev;
+    __device__ __forceinline__ void init() { st.clear(); have_prev = false; prev.ok = false; }
+    __device__ __forceinline__ void push(double nu, const Voxel &v)
+    {
+        if (!v.ok) { have_prev = false; return; }
+        if (NEED_BETWEEN) {
+            if (have_prev && prev.B > 0.0 && v.B > 0.0) st.apply(between_voxels(nu, prev, v));
+            prev = v;
+            have_prev = true;
+        }
+        st.apply(voxel_op(nu, v));
+    }
+    __device__ __forceinline__ void result(double &L, double &R) const { L = st.L[0]; R = st.R[0]; }
+};
+
+template <bool NEED_BETWEEN>
+struct OutwardTransferT : OutwardTransfer {
+    __device__ __forceinline__ void push(double nu, const Voxel &v)
+    {
+        if (!v.ok) { have_prev = false; return; }
+        if (NEED_BETWEEN) {
+            if (have_prev && prev.B > 0.0 && v.B > 0.0) {
+                const Between b = between_voxels(nu, v, prev);
+                fold(b.after);
+                if (b.qt) fold_qt(b.Q);
+                fold(b.before);
+            }
+            prev = v;
+            have_prev = true;
+        }
+        fold(voxel_op(nu, v));
+    }
+    __device__ __forceinline__ void result(double &L, double &R) const { L = accL; R = accR; }
+};
+
+template <bool CS, int ORDER, bool BVEC, bool GR>
 __global__ void __launch_bounds__(128) render_map_kernel(const MapArgs a)
 {
+    constexpr bool LERP64 = false;
+    constexpr bool NEED_BETWEEN = BVEC || GR;
     const int64_t ray = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int fi = blockIdx.y;
     const bool has_ray = ray < a.n_rays;
@@ -89,10 +134,10 @@ __global__ void __launch_bounds__(128) render_map_kernel(const MapArgs a)
 
     State s;
     s.rx = s.ry = s.rz = s.kx = s.ky = s.kz = nan("");
-    float sx0 = 0.f, sy0 = 0.f, sz0 = 0.f;   // ray_start as float32 (gpu_raytrace.py:650)
+    float px = 0.f, py = 0.f, pz = 0.f;   // previous VALID sample position, float32; starts at ray_start
     if (has_ray) {
         s.rx = a.x_start[ray]; s.ry = a.y_start[ray]; s.rz = a.z_start[ray];
-        sx0 = (float)s.rx; sy0 = (float)s.ry; sz0 = (float)s.rz;
+        px = (float)s.rx; py = (float)s.ry; pz = (float)s.rz;     // _as_float32_c(ray_start), gpu_raytrace.py:650
         const double kc0 = start_kc(C, s.rx, s.ry, s.rz, fp.omega0);
         if (a.kvec) {
             s.kx = a.kvec[ray * 3 + 0] * kc0; s.ky = a.kvec[ray * 3 + 1] * kc0; s.kz = a.kvec[ray * 3 + 2] * kc0;
@@ -105,13 +150,11 @@ __global__ void __launch_bounds__(128) render_map_kernel(const MapArgs a)
     unsigned long long moved_steps = 0;
     int64_t next_rec = 0;
 
-    OnlineTransfer<1> fwd;
-    OutwardTransfer rev;
-    fwd.init();
-    rev.init();
-    float px = sx0, py = sy0, pz = sz0;   // previous VALID sample position (float32)
+    typename std::conditional<ORDER == RTGRFF_ORDER_RECORD, RecordTransfer<NEED_BETWEEN>,
+                              OutwardTransferT<NEED_BETWEEN>>::type tr;
+    tr.init();
     bool first = true;
-    bool tail_done = false;               // a frozen ray repeats the same record: ds = 0 -> empty voxel
+    bool tail_done = !has_ray;            // a frozen ray repeats the same record: ds = 0 -> empty voxel
 
     for (int64_t i = 0; i < fp.n_steps; ++i) {
         if (alive) {
@@ -124,7 +167,7 @@ __global__ void __launch_bounds__(128) render_map_kernel(const MapArgs a)
         }
         if (i == next_rec) {
             next_rec += fp.stride;
-            if (has_ray && !tail_done) {
+            if (!tail_done) {
                 // --- sampler (float32, gpu_raytrace.py:642-650) ---
                 const float x = (float)s.rx, y = (float)s.ry, z = (float)s.rz, sv = (float)s_step;
                 if (sample_valid(x, y, z, sv)) {
@@ -134,7 +177,7 @@ __global__ void __launch_bounds__(128) render_map_kernel(const MapArgs a)
                     // --- Parms packing rules (script/resample_with_ray_tracing.py:472-501) ---
                     if (isfinite(f.ne) && isfinite(f.te) && isfinite(f.b)) {
                         double th = 90.0, bmag = (double)f.b;
-                        if (a.use_bvec) {
+                        if (BVEC) {
                             const float3 bv = sample_bvec(a.bcube, a.fg, x, y, z);
                             const double dx = (double)x - (double)px, dy = (double)y - (double)py, dz = (double)z - (double)pz;
                             const double dn = sqrt(dx * dx + dy * dy + dz * dz);
@@ -143,9 +186,7 @@ __global__ void __launch_bounds__(128) render_map_kernel(const MapArgs a)
                             const double c = -((double)bv.x * dx + (double)bv.y * dy + (double)bv.z * dz) / (bmag * dn);
                             th = (bmag > 0.0 && dn > 0.0) ? acos(fmin(1.0, fmax(-1.0, c))) * (180.0 / kPi) : 90.0;
                         }
-                        const Voxel v = make_voxel((double)ds, (double)f.te, (double)f.ne, bmag, th, a.em_flag, a.s_max);
-                        if (a.order == RTGRFF_ORDER_RECORD) fwd.push(fp.nu, v);
-                        else rev.push(fp.nu, v);
+                        tr.push(fp.nu, make_voxel((double)ds, (double)f.te, (double)f.ne, bmag, th, a.em_flag, a.s_max));
                     }
                     px = x; py = y; pz = z;
                     first = false;
@@ -157,9 +198,9 @@ __global__ void __launch_bounds__(128) render_map_kernel(const MapArgs a)
         if (!__any_sync(0xffffffffu, alive)) break;
     }
     if (has_ray) {
-        double tb, vi;
-        if (a.order == RTGRFF_ORDER_RECORD) tb_vi(fwd.st.L[0], fwd.st.R[0], fp.nu, a.area, tb, vi);
-        else tb_vi(rev.accL, rev.accR, fp.nu, a.area, tb, vi);
+        double tb, vi, IL, IR;
+        tr.result(IL, IR);
+        tb_vi(IL, IR, fp.nu, a.area, tb, vi);
         a.tb[(size_t)fi * a.n_rays + ray] = tb;
         a.vi[(size_t)fi * a.n_rays + ray] = vi;
     }

@@ -150,6 +150,8 @@ int rtgrff_ctx_create(int device, void *stream, rtgrff_ctx **out)
         RT_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         c->own_stream = true;
     }
+    RT_CUDA(cudaEventCreate(&c->ev0));
+    RT_CUDA(cudaEventCreate(&c->ev1));
     *out = c;
     return RTGRFF_OK;
 }
@@ -163,6 +165,8 @@ int rtgrff_ctx_destroy(rtgrff_ctx *c)
                       &c->smp_ds, &c->smp_s, &c->smp_valid, &c->in0, &c->in1, &c->in2, &c->in3, &c->out0, &c->out1,
                       &c->out2, &c->out3, &c->out4, &c->out5, &c->stage, &c->counters};
     for (DevBuf *b : bufs) b->release();
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return RTGRFF_OK;
@@ -176,6 +180,16 @@ int rtgrff_ctx_synchronize(rtgrff_ctx *c)
 }
 
 int64_t rtgrff_ctx_launch_count(const rtgrff_ctx *c) { return c ? c->launches : 0; }
+
+double rtgrff_ctx_last_kernel_ms(rtgrff_ctx *c)
+{
+    if (!c || !c->ev_valid) return -1.0;
+    float ms = -1.0f;
+    if (cudaSetDevice(c->device) != cudaSuccess) return -1.0;
+    if (cudaEventSynchronize(c->ev1) != cudaSuccess) return -1.0;
+    if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) != cudaSuccess) return -1.0;
+    return (double)ms;
+}
 
 int rtgrff_set_omega_cube(rtgrff_ctx *c, const double *omega_pe, int nx, int ny, int nz, const double geom[12],
                           int on_device)
@@ -273,6 +287,7 @@ int rtgrff_trace(rtgrff_ctx *c, int64_t n_rays, const double *x_start, const dou
     a.active_steps = c->counters.as<unsigned long long>();
     const dim3 grid(blocks_for(n_rays, 128)), block(128);
     const int l64 = trace_variant();
+    RT_CUDA(cudaEventRecord(c->ev0, c->stream));
     if (trace_cs) {
         if (l64) trace_rays_kernel<true, true><<<grid, block, 0, c->stream>>>(a);
         else trace_rays_kernel<true, false><<<grid, block, 0, c->stream>>>(a);
@@ -281,6 +296,8 @@ int rtgrff_trace(rtgrff_ctx *c, int64_t n_rays, const double *x_start, const dou
         else trace_rays_kernel<false, false><<<grid, block, 0, c->stream>>>(a);
     }
     RT_TRY(launched(c, "trace_rays_kernel"));
+    RT_CUDA(cudaEventRecord(c->ev1, c->stream));
+    c->ev_valid = true;
     if (r_record) {
         RT_TRY(c->out0.reserve((size_t)n_rec * 3 * nb));
         records_to_aos_kernel<<<blocks_for(n_rec * n_rays * 3, 256), 256, 0, c->stream>>>(
@@ -310,8 +327,11 @@ static int run_sampler(rtgrff_ctx *c, SampleArgs &a, double r_sun_cm, double fil
     unsigned int blocks = blocks_for((int64_t)n, 256);
     const unsigned int cap = (unsigned int)c->sm_count * 64;
     if (blocks > cap) blocks = cap;
+    RT_CUDA(cudaEventRecord(c->ev0, c->stream));
     sample_paths_kernel<<<blocks, 256, 0, c->stream>>>(a);
     RT_TRY(launched(c, "sample_paths_kernel"));
+    RT_CUDA(cudaEventRecord(c->ev1, c->stream));
+    c->ev_valid = true;
     c->smp_n = a.n_rec; c->smp_rays = a.n_rays;
     return RTGRFF_OK;
 }
@@ -381,8 +401,11 @@ static int run_slice(rtgrff_ctx *c, int npix, int nz, int nf, const double *rpar
     a.rl = c->out0.as<double>(); a.status = c->out1.as<int32_t>();
     a.npix = npix; a.nz = nz; a.nf = nf;
     const int64_t warps = (int64_t)npix * nf;
+    RT_CUDA(cudaEventRecord(c->ev0, c->stream));
     grff_slice_kernel<<<blocks_for(warps * 32, 128), 128, 0, c->stream>>>(a);
     RT_TRY(launched(c, "grff_slice_kernel"));
+    RT_CUDA(cudaEventRecord(c->ev1, c->stream));
+    c->ev_valid = true;
     RT_TRY(d2h(c, rl, c->out0.p, ob));
     if (status) RT_TRY(d2h(c, status, c->out1.p, (size_t)npix * sizeof(int32_t)));
     RT_CUDA(cudaStreamSynchronize(c->stream));
@@ -434,8 +457,11 @@ int rtgrff_emission_traced(rtgrff_ctx *c, double pixel_area_cm2, double freq0_hz
     a.area = pixel_area_cm2; a.freq0 = freq0_hz; a.log_step = freq_log_step;
     a.n_freq = n_freq; a.em_flag = em_flag; a.s_max = s_max;
     a.tb = c->out0.as<double>(); a.vi = c->out1.as<double>();
+    RT_CUDA(cudaEventRecord(c->ev0, c->stream));
     emission_rays_kernel<<<blocks_for((int64_t)n, 128), 128, 0, c->stream>>>(a);
     RT_TRY(launched(c, "emission_rays_kernel"));
+    RT_CUDA(cudaEventRecord(c->ev1, c->stream));
+    c->ev_valid = true;
     RT_TRY(d2h(c, tb, c->out0.p, n * sizeof(double)));
     RT_TRY(d2h(c, vi, c->out1.p, n * sizeof(double)));
     RT_CUDA(cudaStreamSynchronize(c->stream));
@@ -452,6 +478,7 @@ int rtgrff_render_map(rtgrff_ctx *c, int64_t n_rays, const double *x_start, cons
     if (!c->has_fcube) return fail(RTGRFF_ENOCUBE, "rtgrff_set_field_cubes has not been called");
     if (use_bvec && !c->has_bvec) return fail(RTGRFF_ENOCUBE, "use_bvec needs bx,by,bz in rtgrff_set_field_cubes");
     if (n_rays < 0 || n_freq <= 0 || n_freq > 65535 || !freqs || !tb || !vi) return fail(RTGRFF_EINVAL, "bad arguments");
+    if (voxel_order != RTGRFF_ORDER_RECORD && voxel_order != RTGRFF_ORDER_REVERSED) return fail(RTGRFF_EINVAL, "bad voxel_order");
     if (n_rays > 0 && (!x_start || !y_start || !z_start)) return fail(RTGRFF_EINVAL, "null start arrays");
     if (stats) stats[0] = stats[1] = 0;
     if (n_rays == 0) return RTGRFF_OK;
@@ -497,15 +524,25 @@ int rtgrff_render_map(rtgrff_ctx *c, int64_t n_rays, const double *x_start, cons
     a.tb = dtb; a.vi = dvi;
     a.active_steps = c->counters.as<unsigned long long>();
     const dim3 grid(blocks_for(n_rays, 128), (unsigned int)n_freq), block(128);
-    const int l64 = trace_variant();
-    if (trace_cs) {
-        if (l64) render_map_kernel<true, true><<<grid, block, 0, c->stream>>>(a);
-        else render_map_kernel<true, false><<<grid, block, 0, c->stream>>>(a);
-    } else {
-        if (l64) render_map_kernel<false, true><<<grid, block, 0, c->stream>>>(a);
-        else render_map_kernel<false, false><<<grid, block, 0, c->stream>>>(a);
+    const bool gr = !(em_flag & 1);
+    RT_CUDA(cudaEventRecord(c->ev0, c->stream));
+    const int variant = (trace_cs ? 8 : 0) | (voxel_order == RTGRFF_ORDER_REVERSED ? 4 : 0) | (use_bvec ? 2 : 0) | (gr ? 1 : 0);
+#define RT_MAP_CASE(v, CS, ORD, BV, GR)                                                                  \
+    case v: render_map_kernel<CS, ORD, BV, GR><<<grid, block, 0, c->stream>>>(a); break;
+    switch (variant) {
+        RT_MAP_CASE(0, false, 0, false, false) RT_MAP_CASE(1, false, 0, false, true)
+        RT_MAP_CASE(2, false, 0, true, false) RT_MAP_CASE(3, false, 0, true, true)
+        RT_MAP_CASE(4, false, 1, false, false) RT_MAP_CASE(5, false, 1, false, true)
+        RT_MAP_CASE(6, false, 1, true, false) RT_MAP_CASE(7, false, 1, true, true)
+        RT_MAP_CASE(8, true, 0, false, false) RT_MAP_CASE(9, true, 0, false, true)
+        RT_MAP_CASE(10, true, 0, true, false) RT_MAP_CASE(11, true, 0, true, true)
+        RT_MAP_CASE(12, true, 1, false, false) RT_MAP_CASE(13, true, 1, false, true)
+        RT_MAP_CASE(14, true, 1, true, false) RT_MAP_CASE(15, true, 1, true, true)
     }
+#undef RT_MAP_CASE
     RT_TRY(launched(c, "render_map_kernel"));
+    RT_CUDA(cudaEventRecord(c->ev1, c->stream));
+    c->ev_valid = true;
     if (!out_on_device) {
         RT_TRY(d2h(c, tb, dtb, (size_t)n_freq * nb));
         RT_TRY(d2h(c, vi, dvi, (size_t)n_freq * nb));

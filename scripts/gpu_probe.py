@@ -1,0 +1,87 @@
+#!/usr/bin/env python
+"""Quick GPU probe: parity numbers and raw kernel timings of each stage (development aid)."""
+import os
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+from raytracinggrff_b200 import RaySession, synthetic  # noqa: E402
+from oracle import oracle  # noqa: E402
+
+
+def timeit(fn, n=3):
+    fn()
+    best = 1e9
+    for _ in range(n):
+        t0 = time.perf_counter()
+        fn()
+        best = min(best, time.perf_counter() - t0)
+    return best
+
+
+def main():
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    print("variant LERP64 =", os.environ.get("RTGRFF_LERP64", "0"))
+    ses = RaySession(0)
+    if which in ("all", "c3"):
+        c = synthetic.corona_cube(128, 3.0)
+        ses.set_omega_cube(c["omega_pe"], c["x_grid"], c["y_grid"], c["z_grid"])
+        xs, ys, zs, kv = synthetic.ray_launch_geometry(64, 1.44, 3.0)
+        r, s, act = ses.trace(75e6, xs, ys, zs, kv, 6e-3, 5000, 10, True, 2.0)
+        t0 = time.perf_counter()
+        r_ref, cs_ref, act_ref = oracle.ray_trace(c["omega_pe"], c["x_grid"], c["y_grid"], c["z_grid"], 75e6, xs, ys, zs,
+                                                  kv, 6e-3, 5000, 10, True, perturb_ratio=2, return_active=True)
+        t_cpu = time.perf_counter() - t0
+        s_ref = np.array(cs_ref)
+        ok = np.isfinite(s_ref)
+        print(f"C3 parity: max|dr|={np.nanmax(np.abs(r - r_ref)):.3e}  max rel dS={np.max(np.abs(s[ok]-s_ref[ok])/s_ref[ok]):.3e} "
+              f"active gpu/cpu={act}/{act_ref}  oracle {t_cpu:.2f}s ({os.cpu_count()} threads)")
+        t = timeit(lambda: ses.trace(75e6, xs, ys, zs, kv, 6e-3, 5000, 10, True, 2.0, fetch=False))
+        print(f"C3 trace (cs): {t*1e3:.1f} ms  nominal {4096*5000/t:.3e} ray-steps/s  active {act/t:.3e}")
+        t = timeit(lambda: ses.trace(75e6, xs, ys, zs, kv, 6e-3, 5000, 10, False, 2.0, fetch=False))
+        print(f"C3 trace (no cs): {t*1e3:.1f} ms  nominal {4096*5000/t:.3e} ray-steps/s")
+    if which in ("all", "c4"):
+        c = synthetic.corona_cube(256, 3.0)
+        ses.set_omega_cube(c["omega_pe"], c["x_grid"], c["y_grid"], c["z_grid"])
+        ses.set_field_cubes(c["x_grid"], c["y_grid"], c["z_grid"], c["ne"], c["te"], c["b"])
+        xs, ys, zs, kv = synthetic.ray_launch_geometry(512, 1.44, 3.0)
+        for f in (75e6, 300e6):
+            p = synthetic.frequency_scaled_params(f)
+            _, _, act = ses.trace(f, xs, ys, zs, kv, p["dt"], p["n_steps"], max(p["record_stride"], 50), True, 2.0, fetch=False)
+            t = timeit(lambda: ses.trace(f, xs, ys, zs, kv, p["dt"], p["n_steps"], max(p["record_stride"], 50), True, 2.0, fetch=False), n=2)
+            nom = xs.size * p["n_steps"]
+            print(f"C4 trace f={f/1e6:.0f}MHz T={p['n_steps']}: {t*1e3:.1f} ms nominal {nom/t:.3e} active {act/t:.3e} ray-steps/s "
+                  f"(alg {act*1536/t/1e9:.0f} GB/s)")
+            area = (2 * 1.44 / 512 * 6.957e10) ** 2
+            fp = [(f, p["dt"], p["n_steps"], p["record_stride"])]
+            _, _, st = ses.render_map(xs, ys, zs, fp, kvec_in_norm=kv, pixel_area_cm2=area)
+            t = timeit(lambda: ses.render_map(xs, ys, zs, fp, kvec_in_norm=kv, pixel_area_cm2=area), n=2)
+            print(f"C4 fused f={f/1e6:.0f}MHz: {t*1e3:.1f} ms nominal {st['nominal_ray_steps']/t:.3e} active {st['active_ray_steps']/t:.3e} ray-steps/s")
+    if which in ("ncu_trace", "ncu_fused"):
+        c = synthetic.corona_cube(256, 3.0)
+        ses.set_omega_cube(c["omega_pe"], c["x_grid"], c["y_grid"], c["z_grid"])
+        ses.set_field_cubes(c["x_grid"], c["y_grid"], c["z_grid"], c["ne"], c["te"], c["b"])
+        xs, ys, zs, kv = synthetic.ray_launch_geometry(512, 1.44, 3.0)
+        f = 75e6
+        p = synthetic.frequency_scaled_params(f)
+        if which == "ncu_trace":
+            _, _, act = ses.trace(f, xs, ys, zs, kv, p["dt"], p["n_steps"], p["record_stride"], True, 2.0, fetch=False)
+            print("active", act)
+        else:
+            area = (2 * 1.44 / 512 * 6.957e10) ** 2
+            _, _, st = ses.render_map(xs, ys, zs, [(f, p["dt"], p["n_steps"], p["record_stride"])], kvec_in_norm=kv, pixel_area_cm2=area)
+            print(st)
+    if which in ("all", "c1"):
+        args = synthetic.los_sampler_case(256, 256, 128, seed=0)
+        ses.set_field_cubes(args[0], args[1], args[2], args[3], args[4], args[5])
+        t = timeit(lambda: ses.sample(args[6], args[7], args[8], 6.957e10))
+        print(f"C1 sampler e2e (H2D+kernel+D2H): {t*1e3:.1f} ms  {256*256*256/t:.3e} samples/s")
+    print("launches", ses.ctx.launch_count)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,61 @@
+"""CPU: the multi-GPU sharding / gather logic with world_size 2 and 3 over gloo."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from raytracinggrff_b200 import dist as rdist
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n_rows, n_x, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        idx, rows = rdist.shard_rays(n_x, n_rows, world, rank)
+        # stand-in for the renderer: value = f(frequency, flat ray index)
+        mr = rdist.max_rows_per_rank(n_rows, world)
+        local = torch.full((2, mr, n_x), -1.0, dtype=torch.float64)
+        vals = torch.from_numpy(idx.astype(np.float64)).reshape(len(rows), n_x)
+        local[0, :len(rows)] = vals
+        local[1, :len(rows)] = 10.0 * vals
+        full = rdist.gather_rows(local, n_rows)
+        q.put((rank, full.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_rows", [(2, 8), (2, 7), (3, 10)])
+def test_interleaved_rows_gather(world, n_rows):
+    n_x = 5
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_rows, n_x, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=60) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    expect = np.arange(n_rows * n_x, dtype=np.float64).reshape(n_rows, n_x)
+    for rank, full in outs:
+        np.testing.assert_array_equal(full[0], expect)
+        np.testing.assert_array_equal(full[1], 10.0 * expect)
+
+
+def test_shard_covers_every_ray_once():
+    for world in (1, 2, 4, 8):
+        seen = np.concatenate([rdist.shard_rays(16, 37, world, r)[0] for r in range(world)])
+        assert np.array_equal(np.sort(seen), np.arange(16 * 37))
+        sizes = [len(rdist.rows_of_rank(37, world, r)) for r in range(world)]
+        assert max(sizes) - min(sizes) <= 1 and max(sizes) == rdist.max_rows_per_rank(37, world)
