@@ -156,3 +156,16 @@ def los_sampler_case(n_pix=256, n_steps=256, grid_n=128, seed=0):
     r_record = origin[None, :, :] + s[:, :, None] * dirs[None, :, :]
     s_arr = np.ones((n_steps, n_rays), dtype=np.float32)
     return g, g.copy(), g.copy(), ne, te, b, r_record, s_arr, origin
+
+
+def tile_order(n_x, n_y, tile_w=8, tile_h=4):
+    """Permutation of the flat pixel indices p = i*n_x + j that walks the image in tile_w x tile_h
+    pixel tiles (row-major inside a tile): with one thread per ray, a warp of 32 consecutive rays
+    then covers an 8x4 pixel patch instead of a 32x1 strip, so its gathers touch fewer cube cells.
+    Returns `perm` such that rays[perm] is the tiled order; scatter results back with
+    ``out[perm] = out_tiled``."""
+    i = np.arange(n_y)[:, None]
+    j = np.arange(n_x)[None, :]
+    tiles_x = (n_x + tile_w - 1) // tile_w
+    key = ((i // tile_h) * tiles_x + (j // tile_w)) * (tile_w * tile_h) + (i % tile_h) * tile_w + (j % tile_w)
+    return np.argsort(key.ravel(), kind="stable")

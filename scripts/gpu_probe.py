@@ -61,6 +61,17 @@ def main():
             _, _, st = ses.render_map(xs, ys, zs, fp, kvec_in_norm=kv, pixel_area_cm2=area)
             t = timeit(lambda: ses.render_map(xs, ys, zs, fp, kvec_in_norm=kv, pixel_area_cm2=area), n=2)
             print(f"C4 fused f={f/1e6:.0f}MHz: {t*1e3:.1f} ms nominal {st['nominal_ray_steps']/t:.3e} active {st['active_ray_steps']/t:.3e} ray-steps/s")
+    if which == "tile":
+        c = synthetic.corona_cube(256, 3.0)
+        ses.set_omega_cube(c["omega_pe"], c["x_grid"], c["y_grid"], c["z_grid"])
+        xs, ys, zs, kv = synthetic.ray_launch_geometry(512, 1.44, 3.0)
+        p = synthetic.frequency_scaled_params(75e6)
+        for tw, th in ((32, 1), (16, 2), (8, 4), (4, 8)):
+            perm = synthetic.tile_order(512, 512, tw, th)
+            a, b, cz = xs[perm], ys[perm], zs[perm]
+            _, _, act = ses.trace(75e6, a, b, cz, None, p["dt"], p["n_steps"], 50, True, 2.0, fetch=False)
+            t = timeit(lambda: ses.trace(75e6, a, b, cz, None, p["dt"], p["n_steps"], 50, True, 2.0, fetch=False), n=2)
+            print(f"tile {tw}x{th}: {t*1e3:.1f} ms (kernel {ses.ctx.last_kernel_ms:.1f} ms) active {act/t:.3e} ray-steps/s")
     if which in ("ncu_trace", "ncu_fused"):
         c = synthetic.corona_cube(256, 3.0)
         ses.set_omega_cube(c["omega_pe"], c["x_grid"], c["y_grid"], c["z_grid"])
