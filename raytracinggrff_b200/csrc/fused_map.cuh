@@ -13,7 +13,7 @@
 
 #include "grff.cuh"
 #include "los_sampler.cuh"
-#include "ray_integrator.cuh"
+#include "trace_kernel.cuh"
 
 #include <type_traits>
 
@@ -121,16 +121,18 @@ struct OutwardTransferT : OutwardTransfer {
     __device__ __forceinline__ void result(double &L, double &R) const { L = accL; R = accR; }
 };
 
-template <bool CS, int ORDER, bool BVEC, bool GR>
+template <bool CS, int ORDER, bool BVEC, bool GR, int MODE>
 __global__ void __launch_bounds__(128) render_map_kernel(const MapArgs a)
 {
-    constexpr bool LERP64 = false;
     constexpr bool NEED_BETWEEN = BVEC || GR;
     const int64_t ray = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int fi = blockIdx.y;
     const bool has_ray = ray < a.n_rays;
     const RayCube &C = a.cube;
     const FreqDev fp = a.freqs[fi];
+    const StepConst K = make_step_const(C, fp.dt, a.perturb_ratio);
+    Cell cache;
+    cache.off = -1;
 
     State s;
     s.rx = s.ry = s.rz = s.kx = s.ky = s.kz = nan("");
@@ -158,12 +160,8 @@ __global__ void __launch_bounds__(128) render_map_kernel(const MapArgs a)
 
     for (int64_t i = 0; i < fp.n_steps; ++i) {
         if (alive) {
-            const State s0 = s;
-            s = rk4_step<LERP64>(C, s0, fp.dt);
-            if (CS) s_step = cross_section_ratio<LERP64>(C, s0, s, fp.dt, a.perturb_ratio);
-            const bool moved = in_cube(C, s0.rx, s0.ry, s0.rz) && state_differs(s, s0);
-            moved_steps += moved ? 1ull : 0ull;
-            alive = moved;
+            alive = advance_ray<CS, MODE>(C, K, cache, s, fp.dt, a.perturb_ratio, s_step);
+            moved_steps += alive ? 1ull : 0ull;
         }
         if (i == next_rec) {
             next_rec += fp.stride;

@@ -156,82 +156,6 @@ __device__ __forceinline__ bool state_differs(const State &a, const State &b)
     return (a.rx != b.rx) | (a.ry != b.ry) | (a.rz != b.rz) | (a.kx != b.kx) | (a.ky != b.ky) | (a.kz != b.kz);
 }
 
-struct TraceArgs {
-    RayCube cube;
-    int64_t n_rays;
-    const double *x_start, *y_start, *z_start;  // device, (n_rays)
-    const double *kvec;                          // device, (n_rays,3) or nullptr -> (0,0,-1)
-    double omega0, dt, perturb_ratio;
-    int64_t n_steps, stride, n_rec;
-    int s_mode;
-    double *rec_pos;  // device [rec][3][ray]
-    double *rec_s;    // device [rec][ray] (only when CS)
-    unsigned long long *active_steps;
-};
-
-template <bool CS, bool LERP64>
-__global__ void __launch_bounds__(128) trace_rays_kernel(const TraceArgs a)
-{
-    const int64_t ray = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool has_ray = ray < a.n_rays;
-    const RayCube &C = a.cube;
-    State s;
-    s.rx = s.ry = s.rz = s.kx = s.ky = s.kz = nan("");
-    if (has_ray) {
-        s.rx = a.x_start[ray]; s.ry = a.y_start[ray]; s.rz = a.z_start[ray];
-        const double kc0 = start_kc(C, s.rx, s.ry, s.rz, a.omega0);
-        if (a.kvec) {
-            s.kx = a.kvec[ray * 3 + 0] * kc0; s.ky = a.kvec[ray * 3 + 1] * kc0; s.kz = a.kvec[ray * 3 + 2] * kc0;
-        } else {
-            s.kx = 0.0 * kc0; s.ky = 0.0 * kc0; s.kz = -kc0;
-        }
-    }
-    bool alive = has_ray;
-    double s_step = 0.0, s_cum = 1.0;
-    unsigned long long moved_steps = 0;
-    int64_t rec = 0, next_rec = 0;
-    const size_t n = (size_t)a.n_rays;
-
-    for (int64_t i = 0; i < a.n_steps; ++i) {
-        if (alive) {
-            const State s0 = s;
-            s = rk4_step<LERP64>(C, s0, a.dt);
-            if (CS) {
-                s_step = cross_section_ratio<LERP64>(C, s0, s, a.dt, a.perturb_ratio);
-                s_cum *= s_step;
-            }
-            // A step that leaves the state untouched (start outside the cube, NaN, omega = 0) repeats
-            // forever with the same S: the ray is frozen from here on.
-            const bool moved = in_cube(C, s0.rx, s0.ry, s0.rz) && state_differs(s, s0);
-            moved_steps += moved ? 1ull : 0ull;
-            alive = moved;
-        }
-        if (i == next_rec) {
-            if (has_ray) {
-                double *o = a.rec_pos + (size_t)rec * 3 * n + (size_t)ray;
-                o[0] = s.rx; o[n] = s.ry; o[2 * n] = s.rz;
-                if (CS) a.rec_s[(size_t)rec * n + (size_t)ray] = (a.s_mode == RTGRFF_S_CUMULATIVE) ? s_cum : s_step;
-            }
-            ++rec;
-            next_rec += a.stride;
-        }
-        if (!__any_sync(0xffffffffu, alive)) break;
-    }
-    // frozen tail: constant records
-    if (has_ray) {
-        const double sv = (a.s_mode == RTGRFF_S_CUMULATIVE) ? s_cum : s_step;
-        for (; rec < a.n_rec; ++rec) {
-            double *o = a.rec_pos + (size_t)rec * 3 * n + (size_t)ray;
-            o[0] = s.rx; o[n] = s.ry; o[2 * n] = s.rz;
-            if (CS) a.rec_s[(size_t)rec * n + (size_t)ray] = sv;
-        }
-    }
-    if (a.active_steps) {
-        for (int off = 16; off > 0; off >>= 1) moved_steps += __shfl_down_sync(0xffffffffu, moved_steps, off);
-        if ((threadIdx.x & 31) == 0 && moved_steps) atomicAdd(a.active_steps, moved_steps);
-    }
-}
-
 // SoA [rec][3][ray] -> AoS (rec, ray, 3), the reference's r_record layout (build_rays.py:248).
 __global__ void records_to_aos_kernel(const double *__restrict__ soa, double *__restrict__ aos,
                                       int64_t n_rec, int64_t n_rays)

@@ -11,6 +11,7 @@
 #include "grff.cuh"
 #include "los_sampler.cuh"
 #include "ray_integrator.cuh"
+#include "trace_kernel.cuh"
 
 namespace rtgrff {
 
@@ -104,11 +105,12 @@ static int launched(rtgrff_ctx *c, const char *what)
 
 static int trace_variant()
 {
-    // RTGRFF_LERP64=1 selects FP64 trilinear arithmetic (default: FP32 lerps on the FP32 cube).
+    // RTGRFF_MODE selects the ray stepper: 0 (default) FP64 master state + FP32 cell-relative RHS with a
+    // register cell cache; 1 FP64 state and RHS, FP32 trilinear arithmetic; 2 FP64 everything.
     static int v = -1;
     if (v < 0) {
-        const char *e = getenv("RTGRFF_LERP64");
-        v = (e && e[0] == '1') ? 1 : 0;
+        const char *e = getenv("RTGRFF_MODE");
+        v = (e && e[0] >= '0' && e[0] <= '2') ? (e[0] - '0') : 0;
     }
     return v;
 }
@@ -286,15 +288,19 @@ int rtgrff_trace(rtgrff_ctx *c, int64_t n_rays, const double *x_start, const dou
     a.rec_s = trace_cs ? c->rec_s.as<double>() : nullptr;
     a.active_steps = c->counters.as<unsigned long long>();
     const dim3 grid(blocks_for(n_rays, 128)), block(128);
-    const int l64 = trace_variant();
+    int l64 = trace_variant();
+    // the FP32 cell-relative stepper needs every stage within one cell of the step's base cell
+    if (l64 == MODE_FAST32 &&
+        !(max_stage_offset_cells(dt, trace_cs ? perturb_ratio : 0.0, c->wgeom.idx, c->wgeom.idy, c->wgeom.idz) < 0.999))
+        l64 = MODE_F64;
     RT_CUDA(cudaEventRecord(c->ev0, c->stream));
-    if (trace_cs) {
-        if (l64) trace_rays_kernel<true, true><<<grid, block, 0, c->stream>>>(a);
-        else trace_rays_kernel<true, false><<<grid, block, 0, c->stream>>>(a);
-    } else {
-        if (l64) trace_rays_kernel<false, true><<<grid, block, 0, c->stream>>>(a);
-        else trace_rays_kernel<false, false><<<grid, block, 0, c->stream>>>(a);
+#define RT_TRACE_CASE(v, CS, M) \
+    case v: trace_rays_kernel<CS, M><<<grid, block, 0, c->stream>>>(a); break;
+    switch ((trace_cs ? 3 : 0) + l64) {
+        RT_TRACE_CASE(0, false, 0) RT_TRACE_CASE(1, false, 1) RT_TRACE_CASE(2, false, 2)
+        RT_TRACE_CASE(3, true, 0) RT_TRACE_CASE(4, true, 1) RT_TRACE_CASE(5, true, 2)
     }
+#undef RT_TRACE_CASE
     RT_TRY(launched(c, "trace_rays_kernel"));
     RT_CUDA(cudaEventRecord(c->ev1, c->stream));
     c->ev_valid = true;
@@ -528,7 +534,15 @@ int rtgrff_render_map(rtgrff_ctx *c, int64_t n_rays, const double *x_start, cons
     RT_CUDA(cudaEventRecord(c->ev0, c->stream));
     const int variant = (trace_cs ? 8 : 0) | (voxel_order == RTGRFF_ORDER_REVERSED ? 4 : 0) | (use_bvec ? 2 : 0) | (gr ? 1 : 0);
 #define RT_MAP_CASE(v, CS, ORD, BV, GR)                                                                  \
-    case v: render_map_kernel<CS, ORD, BV, GR><<<grid, block, 0, c->stream>>>(a); break;
+    case v:                                                                                              \
+        if (mode == MODE_FAST32) render_map_kernel<CS, ORD, BV, GR, MODE_FAST32><<<grid, block, 0, c->stream>>>(a); \
+        else render_map_kernel<CS, ORD, BV, GR, MODE_F64><<<grid, block, 0, c->stream>>>(a);             \
+        break;
+    int mode = trace_variant() == 0 ? MODE_FAST32 : MODE_F64;
+    for (int f = 0; f < n_freq; ++f)
+        if (!(max_stage_offset_cells(freqs[f].dt, trace_cs ? perturb_ratio : 0.0, c->wgeom.idx, c->wgeom.idy,
+                                     c->wgeom.idz) < 0.999))
+            mode = MODE_F64;
     switch (variant) {
         RT_MAP_CASE(0, false, 0, false, false) RT_MAP_CASE(1, false, 0, false, true)
         RT_MAP_CASE(2, false, 0, true, false) RT_MAP_CASE(3, false, 0, true, true)
