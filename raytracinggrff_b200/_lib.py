@@ -7,13 +7,15 @@ or ``python -m raytracinggrff_b200.build``.
 from __future__ import annotations
 
 import ctypes
+import os
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint8, c_void_p
 from pathlib import Path
 
 import numpy as np
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "librtgrff_b200.so"
+# RTGRFF_LIB overrides the library path (A/B runs of differently tuned builds; development aid)
+LIB_PATH = Path(os.environ["RTGRFF_LIB"]) if os.environ.get("RTGRFF_LIB") else _PKG / "librtgrff_b200.so"
 
 RTGRFF_OK = 0
 RTGRFF_EINVAL = -1

@@ -9,6 +9,15 @@
 
 #include "../../include/rtgrff.h"
 
+// Threads per block / minimum resident blocks per SM of the per-ray kernels (tuned on B200, see
+// profiles/): one thread per ray, small blocks so that finished warps free their slots early.
+#ifndef RT_BLOCK
+#define RT_BLOCK 64
+#endif
+#ifndef RT_MINB
+#define RT_MINB 8
+#endif
+
 namespace rtgrff {
 
 // build_rays.py:29-32 (C / R_S with the reference's rounded constants)

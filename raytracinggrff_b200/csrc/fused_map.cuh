@@ -34,7 +34,7 @@ struct MapArgs {
     const FreqDev *freqs;
     double perturb_ratio, area;
     float r_sun_cm, fill_ne, fill_te, fill_b;
-    int em_flag, s_max, use_bvec, order;
+    int em_flag, s_max, use_bvec, order, cs_every_step;
     double *tb, *vi;                     // [freq][ray]
     unsigned long long *active_steps;
 };
@@ -63,21 +63,6 @@ struct OutwardTransfer {
         const double c = m10 * Q + m11 * p, d = m10 * p + m11 * Q;
         m00 = a; m01 = b; m10 = c; m11 = d;
     }
-    __device__ __forceinline__ void push(double nu, const Voxel &v)
-    {
-        if (!v.ok) { have_prev = false; return; }
-        if (have_prev && prev.B > 0.0 && v.B > 0.0) {
-            // radiation crosses v -> prev: between_voxels(v, prev) lists the events in that order,
-            // folding outwards meets them last-first.
-            const Between b = between_voxels(nu, v, prev);
-            fold(b.after);
-            if (b.qt) fold_qt(b.Q);
-            fold(b.before);
-        }
-        fold(voxel_op(nu, v));
-        prev = v;
-        have_prev = true;
-    }
 };
 
 // NEED_BETWEEN: gyroresonance on or theta from the B vector -> the previous voxel must be kept for
@@ -88,27 +73,29 @@ struct RecordTransfer {
     Voxel prev;
     bool have_prev;
     __device__ __forceinline__ void init() { st.clear(); have_prev = false; prev.ok = false; }
-    __device__ __forceinline__ void push(double nu, const Voxel &v)
+    __device__ __forceinline__ void push(const FreqC &f, const Voxel &v)
     {
         if (!v.ok) { have_prev = false; return; }
         if (NEED_BETWEEN) {
-            if (have_prev && prev.B > 0.0 && v.B > 0.0) st.apply(between_voxels(nu, prev, v));
+            if (have_prev && prev.B > 0.0 && v.B > 0.0) st.apply(between_voxels(f.nu, prev, v));
             prev = v;
             have_prev = true;
         }
-        st.apply(voxel_op(nu, v));
+        st.apply(voxel_op(f, v));
     }
     __device__ __forceinline__ void result(double &L, double &R) const { L = st.L[0]; R = st.R[0]; }
 };
 
 template <bool NEED_BETWEEN>
 struct OutwardTransferT : OutwardTransfer {
-    __device__ __forceinline__ void push(double nu, const Voxel &v)
+    __device__ __forceinline__ void push(const FreqC &f, const Voxel &v)
     {
         if (!v.ok) { have_prev = false; return; }
         if (NEED_BETWEEN) {
             if (have_prev && prev.B > 0.0 && v.B > 0.0) {
-                const Between b = between_voxels(nu, v, prev);
+                // radiation crosses v -> prev: between_voxels(v, prev) lists the events in that order,
+                // folding outwards meets them last-first
+                const Between b = between_voxels(f.nu, v, prev);
                 fold(b.after);
                 if (b.qt) fold_qt(b.Q);
                 fold(b.before);
@@ -116,13 +103,13 @@ struct OutwardTransferT : OutwardTransfer {
             prev = v;
             have_prev = true;
         }
-        fold(voxel_op(nu, v));
+        fold(voxel_op(f, v));
     }
     __device__ __forceinline__ void result(double &L, double &R) const { L = accL; R = accR; }
 };
 
 template <bool CS, int ORDER, bool BVEC, bool GR, int MODE>
-__global__ void __launch_bounds__(128) render_map_kernel(const MapArgs a)
+__global__ void __launch_bounds__(RT_BLOCK, RT_MINB) render_map_kernel(const MapArgs a)
 {
     constexpr bool NEED_BETWEEN = BVEC || GR;
     const int64_t ray = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -131,6 +118,7 @@ __global__ void __launch_bounds__(128) render_map_kernel(const MapArgs a)
     const RayCube &C = a.cube;
     const FreqDev fp = a.freqs[fi];
     const StepConst K = make_step_const(C, fp.dt, a.perturb_ratio);
+    const FreqC fq = make_freq(fp.nu);
     Cell cache;
     cache.off = -1;
 
@@ -160,7 +148,8 @@ __global__ void __launch_bounds__(128) render_map_kernel(const MapArgs a)
 
     for (int64_t i = 0; i < fp.n_steps; ++i) {
         if (alive) {
-            alive = advance_ray<CS, MODE>(C, K, cache, s, fp.dt, a.perturb_ratio, s_step);
+            const bool want_s = CS && (i == next_rec || a.cs_every_step);
+            alive = advance_ray<CS, MODE>(C, K, cache, s, fp.dt, a.perturb_ratio, want_s, s_step);
             moved_steps += alive ? 1ull : 0ull;
         }
         if (i == next_rec) {
@@ -184,7 +173,7 @@ __global__ void __launch_bounds__(128) render_map_kernel(const MapArgs a)
                             const double c = -((double)bv.x * dx + (double)bv.y * dy + (double)bv.z * dz) / (bmag * dn);
                             th = (bmag > 0.0 && dn > 0.0) ? acos(fmin(1.0, fmax(-1.0, c))) * (180.0 / kPi) : 90.0;
                         }
-                        tr.push(fp.nu, make_voxel((double)ds, (double)f.te, (double)f.ne, bmag, th, a.em_flag, a.s_max));
+                        tr.push(fq, make_voxel((double)ds, (double)f.te, (double)f.ne, bmag, th, a.em_flag, a.s_max));
                     }
                     px = x; py = y; pz = z;
                     first = false;

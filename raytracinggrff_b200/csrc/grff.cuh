@@ -68,7 +68,12 @@ __device__ __forceinline__ Voxel make_voxel(double dz, double T, double ne, doub
     v.ok = (dz > 0.0) && (T > 0.0) && (ne > 0.0) && (B >= 0.0) && isfinite(dz) && isfinite(T) &&
            isfinite(ne) && isfinite(B) && isfinite(v.th);
     v.cth = 1.0; v.sth = 0.0;
-    if (v.ok) sincos(v.th, &v.sth, &v.cth);
+    if (v.ok) {
+        // theta = 90 deg is what every reference call site passes (script/...:495): skip the sincos;
+        // the constants are sin/cos of the double nearest to pi/2
+        if (th_deg == 90.0) { v.sth = 1.0; v.cth = 6.123233995736766e-17; }
+        else sincos(v.th, &v.sth, &v.cth);
+    }
     return v;
 }
 
@@ -127,14 +132,68 @@ __device__ __forceinline__ void slab_ab(bool prop, double tau, double src, doubl
     }
 }
 
-// Uniform slab of one voxel.
-__device__ __forceinline__ DiagOp voxel_op(double nu, const Voxel &v)
+// Per-frequency constants hoisted out of the voxel loop.
+struct FreqC {
+    double nu, nu2, inv_nu2, ln_nu;
+};
+
+__device__ __forceinline__ FreqC make_freq(double nu)
 {
-    double tp, lp, aX, bX, aO, bO;
-    const Mode mx = mode_eval<false>(nu, v.ne, v.B, v.T, v.cth, v.sth, -1, v.ff_on, tp, lp);
-    const Mode mo = mode_eval<false>(nu, v.ne, v.B, v.T, v.cth, v.sth, +1, v.ff_on, tp, lp);
-    slab_ab(mx.prop, mx.kap * v.dz, mx.src, aX, bX);
-    slab_ab(mo.prop, mo.kap * v.dz, mo.src, aO, bO);
+    FreqC f;
+    f.nu = nu; f.nu2 = nu * nu; f.inv_nu2 = 1.0 / f.nu2; f.ln_nu = log(nu);
+    return f;
+}
+
+// Uniform slab of one voxel: both magneto-ionic modes at once (same formulas as mode_eval; the
+// quantities common to the two modes — u, v, D, the Coulomb logarithm, the opacity prefactor —
+// are evaluated once).
+__device__ __forceinline__ DiagOp voxel_op(const FreqC &f, const Voxel &v)
+{
+    const double nuB = kNuB * v.B;
+    const double u = nuB * nuB * f.inv_nu2, vv = kNup2 * v.ne * f.inv_nu2;
+    const double omv = 1.0 - vv;
+    double pref = 0.0;
+    if (v.ff_on) {
+        const double lnT = log(v.T);
+        const double lnL = (v.T < 2e5) ? 18.2 + 1.5 * lnT - f.ln_nu : 24.573 + lnT - f.ln_nu;
+        pref = kKff * v.ne * v.ne * kZeta * lnL * f.inv_nu2 / (v.T * sqrt(v.T));
+    }
+    const double srcb = f.nu2 * kKbC2 * v.T;
+    double aX = 0.0, bX = 0.0, aO = 0.0, bO = 0.0;
+    if (u > 0.0) {
+        const double s2 = v.sth * v.sth, c2 = v.cth * v.cth;
+        const double us2 = u * s2;
+        const double sD = sqrt(us2 * us2 + 4.0 * u * omv * omv * c2);
+        const double num0 = us2 + 2.0 * omv * omv, base = 2.0 * omv - us2;
+        // X mode (sigma = -1): cut off for nu <= nu_B or v >= 1 - sqrt(u)
+        if (!(u >= 1.0 || vv >= 1.0 - sqrt(u))) {
+            const double den = base - sD;
+            const double n2 = 1.0 - 2.0 * vv * omv / den;
+            const double F = 2.0 * (-sD * num0 - us2 * us2) / (-sD * den * den);
+            if (n2 > 0.0 && isfinite(n2) && isfinite(F)) {
+                double kap = pref * F / sqrt(n2);
+                if (!(kap > 0.0) || !isfinite(kap)) kap = 0.0;
+                slab_ab(true, kap * v.dz, n2 * srcb, aX, bX);
+            }
+        }
+        // O mode (sigma = +1): cut off for v >= 1
+        if (vv < 1.0) {
+            const double den = base + sD;
+            const double n2 = 1.0 - 2.0 * vv * omv / den;
+            const double F = 2.0 * (sD * num0 - us2 * us2) / (sD * den * den);
+            if (n2 > 0.0 && isfinite(n2) && isfinite(F)) {
+                double kap = pref * F / sqrt(n2);
+                if (!(kap > 0.0) || !isfinite(kap)) kap = 0.0;
+                slab_ab(true, kap * v.dz, n2 * srcb, aO, bO);
+            }
+        }
+    } else if (vv < 1.0) {
+        // B = 0: one refractive index, unpolarised
+        double kap = pref / sqrt(omv);
+        if (!(kap > 0.0) || !isfinite(kap)) kap = 0.0;
+        slab_ab(true, kap * v.dz, omv * srcb, aX, bX);
+        aO = aX; bO = bX;
+    }
     // X is R where cos(theta) >= 0
     return (v.cth >= 0.0) ? DiagOp{aO, aX, bO, bX} : DiagOp{aX, aO, bX, bO};
 }
@@ -273,6 +332,7 @@ __global__ void __launch_bounds__(128) grff_slice_kernel(const SliceArgs a)
     const int pix = (int)(warp / a.nf), f = (int)(warp % a.nf);
     const double *R = a.rparms + (size_t)pix * 3;
     const double nu = R[1] * pow(10.0, R[2] * (double)f);
+    const FreqC fq = make_freq(nu);
     const double *P = a.parms + (size_t)pix * 15 * a.nz;
     PolState<3> st;
     st.clear();
@@ -289,7 +349,7 @@ __global__ void __launch_bounds__(128) grff_slice_kernel(const SliceArgs a)
                     const Voxel pv = load_voxel(P + (size_t)(k - 1) * 15);
                     if (pv.ok && pv.B > 0.0 && v.B > 0.0) { bt = between_voxels(nu, pv, v); has_bt = true; }
                 }
-                op = voxel_op(nu, v);
+                op = voxel_op(fq, v);
             }
         }
         const bool any_qt = __any_sync(0xffffffffu, has_bt && bt.qt);
@@ -345,11 +405,11 @@ struct OnlineTransfer {
     Voxel prev;
     bool have_prev;
     __device__ __forceinline__ void init() { st.clear(); have_prev = false; prev.ok = false; }
-    __device__ __forceinline__ void push(double nu, const Voxel &v)
+    __device__ __forceinline__ void push(const FreqC &f, const Voxel &v)
     {
         if (!v.ok) { have_prev = false; return; }
-        if (have_prev && prev.B > 0.0 && v.B > 0.0) st.apply(between_voxels(nu, prev, v));
-        st.apply(voxel_op(nu, v));
+        if (have_prev && prev.B > 0.0 && v.B > 0.0) st.apply(between_voxels(f.nu, prev, v));
+        st.apply(voxel_op(f, v));
         prev = v;
         have_prev = true;
     }
@@ -385,6 +445,7 @@ __global__ void __launch_bounds__(128) emission_rays_kernel(const EmissionArgs a
     const int64_t ray = q % a.n_rays;
     const int f = (int)(q / a.n_rays);
     const double nu = a.freq0 * pow(10.0, a.log_step * (double)f);
+    const FreqC fq = make_freq(nu);
     OnlineTransfer<1> tr;
     tr.init();
     for (int64_t rec = 0; rec < a.n_rec; ++rec) {
@@ -392,7 +453,7 @@ __global__ void __launch_bounds__(128) emission_rays_kernel(const EmissionArgs a
         if (!a.valid[o]) continue;
         const float ne = a.ne[o], te = a.te[o], b = a.b[o];
         if (!(isfinite(ne) && isfinite(te) && isfinite(b))) continue;
-        tr.push(nu, make_voxel((double)a.ds[o], (double)te, (double)ne, (double)b, 90.0, a.em_flag, a.s_max));
+        tr.push(fq, make_voxel((double)a.ds[o], (double)te, (double)ne, (double)b, 90.0, a.em_flag, a.s_max));
     }
     double tb, vi;
     tb_vi(tr.st.L[0], tr.st.R[0], nu, a.area, tb, vi);

@@ -169,14 +169,14 @@ __device__ __forceinline__ RkSum rk4_32(const RayCube &C, const StepConst &K, in
 
 template <bool CS, bool EDGE>
 __device__ __forceinline__ void step32_body(const RayCube &C, const StepConst &K, Cell &cache, State &s, int bi, int bj,
-                                            int bk, float px, float py, float pz, double &s_step)
+                                            int bk, float px, float py, float pz, bool want_s, double &s_step)
 {
     const int base_off = (bi * C.ny + bj) * C.nz + bk;
     const float kx = (float)s.kx, ky = (float)s.ky, kz = (float)s.kz;
     const RkSum c = rk4_32<EDGE>(C, K, bi, bj, bk, base_off, cache, px, py, pz, kx, ky, kz);
     s.rx = fma((double)c.vx, K.c6, s.rx); s.ry = fma((double)c.vy, K.c6, s.ry); s.rz = fma((double)c.vz, K.c6, s.rz);
     s.kx = fma((double)c.gx, -K.c6, s.kx); s.ky = fma((double)c.gy, -K.c6, s.ky); s.kz = fma((double)c.gz, -K.c6, s.kz);
-    if (CS) {
+    if (CS && want_s) {
         // build_rays.py:209-239 with d = r_pert' - r_central' = eps*e + c6*(sum_v_pert - sum_v_central)
         const float dx = K.c6r * c.vx, dy = K.c6r * c.vy, dz = K.c6r * c.vz;
         const float nrd = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
@@ -206,10 +206,11 @@ __device__ __forceinline__ void step32_body(const RayCube &C, const StepConst &K
     }
 }
 
-// One full step of the master state `s` (which must be inside the cube): central RK4, optional
-// cross-section ratio.  Returns true if the state changed.
+// One full step of the master state `s` (which must be inside the cube): central RK4 and, when
+// `want_s` (warp-uniform), the cross-section ratio of this step.  Returns true if the state changed.
 template <bool CS>
-__device__ __forceinline__ bool step32(const RayCube &C, const StepConst &K, Cell &cache, State &s, double &s_step)
+__device__ __forceinline__ bool step32(const RayCube &C, const StepConst &K, Cell &cache, State &s, bool want_s,
+                                       double &s_step)
 {
     // split the master position into base cell + fraction (FP64 -> FP32 once per step)
     const double fx = (s.rx - C.x0) * C.idx, fy = (s.ry - C.y0) * C.idy, fz = (s.rz - C.z0) * C.idz;
@@ -219,8 +220,8 @@ __device__ __forceinline__ bool step32(const RayCube &C, const StepConst &K, Cel
     // stages and pencil rays stay within one cell of the base cell: only a base cell next to a face
     // can produce an out-of-cube stage
     const bool edge = (bi < 1) | (bi > C.nx - 3) | (bj < 1) | (bj > C.ny - 3) | (bk < 1) | (bk > C.nz - 3);
-    if (edge) step32_body<CS, true>(C, K, cache, s, bi, bj, bk, px, py, pz, s_step);
-    else step32_body<CS, false>(C, K, cache, s, bi, bj, bk, px, py, pz, s_step);
+    if (edge) step32_body<CS, true>(C, K, cache, s, bi, bj, bk, px, py, pz, want_s, s_step);
+    else step32_body<CS, false>(C, K, cache, s, bi, bj, bk, px, py, pz, want_s, s_step);
     return state_differs(s, s0);
 }
 

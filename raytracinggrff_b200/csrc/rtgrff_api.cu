@@ -103,6 +103,18 @@ static int launched(rtgrff_ctx *c, const char *what)
     return RTGRFF_OK;
 }
 
+static int cs_every_step()
+{
+    // RTGRFF_CS_EVERY_STEP=1: trace the two cross-section rays at every step like the reference does,
+    // although only the ratio of a recorded step is ever output (A/B switch; results are identical).
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("RTGRFF_CS_EVERY_STEP");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v;
+}
+
 static int trace_variant()
 {
     // RTGRFF_MODE selects the ray stepper: 0 (default) FP64 master state + FP32 cell-relative RHS with a
@@ -284,10 +296,11 @@ int rtgrff_trace(rtgrff_ctx *c, int64_t n_rays, const double *x_start, const dou
     a.dt = dt; a.perturb_ratio = perturb_ratio;
     a.n_steps = n_steps; a.stride = record_stride; a.n_rec = n_rec;
     a.s_mode = s_mode;
+    a.cs_every_step = cs_every_step();
     a.rec_pos = c->rec_pos.as<double>();
     a.rec_s = trace_cs ? c->rec_s.as<double>() : nullptr;
     a.active_steps = c->counters.as<unsigned long long>();
-    const dim3 grid(blocks_for(n_rays, 128)), block(128);
+    const dim3 grid(blocks_for(n_rays, RT_BLOCK)), block(RT_BLOCK);
     int l64 = trace_variant();
     // the FP32 cell-relative stepper needs every stage within one cell of the step's base cell
     if (l64 == MODE_FAST32 &&
@@ -527,9 +540,10 @@ int rtgrff_render_map(rtgrff_ctx *c, int64_t n_rays, const double *x_start, cons
     a.perturb_ratio = perturb_ratio; a.area = pixel_area_cm2;
     a.r_sun_cm = (float)r_sun_cm; a.fill_ne = 0.0f; a.fill_te = 1e4f; a.fill_b = 0.0f;
     a.em_flag = em_flag; a.s_max = s_max; a.use_bvec = use_bvec; a.order = voxel_order;
+    a.cs_every_step = cs_every_step();
     a.tb = dtb; a.vi = dvi;
     a.active_steps = c->counters.as<unsigned long long>();
-    const dim3 grid(blocks_for(n_rays, 128), (unsigned int)n_freq), block(128);
+    const dim3 grid(blocks_for(n_rays, RT_BLOCK), (unsigned int)n_freq), block(RT_BLOCK);
     const bool gr = !(em_flag & 1);
     RT_CUDA(cudaEventRecord(c->ev0, c->stream));
     const int variant = (trace_cs ? 8 : 0) | (voxel_order == RTGRFF_ORDER_REVERSED ? 4 : 0) | (use_bvec ? 2 : 0) | (gr ? 1 : 0);

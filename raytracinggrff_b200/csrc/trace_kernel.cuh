@@ -11,25 +11,31 @@ namespace rtgrff {
 enum { MODE_FAST32 = 0, MODE_F64 = 1, MODE_F64_LERP64 = 2 };
 
 // Advance one ray by one step with the selected stepper.  Returns whether the ray is still alive.
-// A step that leaves the state untouched (outside the cube, NaN, omega = 0) repeats forever with
-// the same S: the ray is frozen from here on (bit-identical to the reference continuing).
+// A step that leaves the state untouched (outside the cube, NaN, omega = 0) repeats forever: the
+// ray is frozen from here on (bit-identical to the reference continuing), and every later step's
+// cross-section ratio is 0/0 = NaN (r_diff = 0 in build_rays.py:217-239).
+//
+// `want_s` (warp-uniform): the reference computes the per-step cross-section ratio at EVERY step
+// but only the value of a recorded step ever leaves ray_trace (build_rays.py:241-244), so in
+// per-step mode the two pencil rays are traced on recorded steps only — same output, 8 of the 12
+// RHS evaluations skipped on the other steps.  Cumulative mode needs every step.
 template <bool CS, int MODE>
 __device__ __forceinline__ bool advance_ray(const RayCube &C, const StepConst &K, Cell &cache, State &s, double dt,
-                                            double perturb_ratio, double &s_step)
+                                            double perturb_ratio, bool want_s, double &s_step)
 {
+    bool moved;
     if (MODE == MODE_FAST32) {
-        if (!in_cube(C, s.rx, s.ry, s.rz)) {
-            if (CS) s_step = nan("");      // r_diff = 0 -> 0/0 in build_rays.py:239
-            return false;
-        }
-        return step32<CS>(C, K, cache, s, s_step);
+        moved = in_cube(C, s.rx, s.ry, s.rz);
+        if (moved) moved = step32<CS>(C, K, cache, s, want_s, s_step);
     } else {
         constexpr bool L64 = (MODE == MODE_F64_LERP64);
         const State s0 = s;
         s = rk4_step<L64>(C, s0, dt);
-        if (CS) s_step = cross_section_ratio<L64>(C, s0, s, dt, perturb_ratio);
-        return in_cube(C, s0.rx, s0.ry, s0.rz) && state_differs(s, s0);
+        if (CS && want_s) s_step = cross_section_ratio<L64>(C, s0, s, dt, perturb_ratio);
+        moved = in_cube(C, s0.rx, s0.ry, s0.rz) && state_differs(s, s0);
     }
+    if (CS && !moved) s_step = nan("");
+    return moved;
 }
 
 struct TraceArgs {
@@ -40,13 +46,14 @@ struct TraceArgs {
     double omega0, dt, perturb_ratio;
     int64_t n_steps, stride, n_rec;
     int s_mode;
+    int cs_every_step;   // 1: trace the pencil rays at every step even when only recorded steps are kept
     double *rec_pos;  // device [rec][3][ray]
     double *rec_s;    // device [rec][ray] (only when CS)
     unsigned long long *active_steps;
 };
 
 template <bool CS, int MODE>
-__global__ void __launch_bounds__(128) trace_rays_kernel(const TraceArgs a)
+__global__ void __launch_bounds__(RT_BLOCK, RT_MINB) trace_rays_kernel(const TraceArgs a)
 {
     const int64_t ray = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool has_ray = ray < a.n_rays;
@@ -73,8 +80,9 @@ __global__ void __launch_bounds__(128) trace_rays_kernel(const TraceArgs a)
 
     for (int64_t i = 0; i < a.n_steps; ++i) {
         if (alive) {
-            alive = advance_ray<CS, MODE>(C, K, cache, s, a.dt, a.perturb_ratio, s_step);
-            if (CS) s_cum *= s_step;
+            const bool want_s = CS && (i == next_rec || a.s_mode == RTGRFF_S_CUMULATIVE || a.cs_every_step);
+            alive = advance_ray<CS, MODE>(C, K, cache, s, a.dt, a.perturb_ratio, want_s, s_step);
+            if (CS && a.s_mode == RTGRFF_S_CUMULATIVE) s_cum *= s_step;
             moved_steps += alive ? 1ull : 0ull;
         }
         if (i == next_rec) {
