@@ -77,7 +77,7 @@ struct RecordTransfer {
     {
         if (!v.ok) { have_prev = false; return; }
         if (NEED_BETWEEN) {
-            if (have_prev && prev.B > 0.0 && v.B > 0.0) st.apply(between_voxels(f.nu, prev, v));
+            if (have_prev && prev.B > 0.0 && v.B > 0.0) st.apply(between_voxels(f, prev, v));
             prev = v;
             have_prev = true;
         }
@@ -95,7 +95,7 @@ struct OutwardTransferT : OutwardTransfer {
             if (have_prev && prev.B > 0.0 && v.B > 0.0) {
                 // radiation crosses v -> prev: between_voxels(v, prev) lists the events in that order,
                 // folding outwards meets them last-first
-                const Between b = between_voxels(f.nu, v, prev);
+                const Between b = between_voxels(f, v, prev);
                 fold(b.after);
                 if (b.qt) fold_qt(b.Q);
                 fold(b.before);
@@ -163,17 +163,21 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_MINB) render_map_kernel(const Map
                     const float ds = __fmul_rn(dist, a.r_sun_cm);
                     // --- Parms packing rules (script/resample_with_ray_tracing.py:472-501) ---
                     if (isfinite(f.ne) && isfinite(f.te) && isfinite(f.b)) {
-                        double th = 90.0, bmag = (double)f.b;
+                        double cth = 6.123233995736766e-17, sth = 1.0, bmag = (double)f.b;   // theta = 90 deg
                         if (BVEC) {
                             const float3 bv = sample_bvec(a.bcube, a.fg, x, y, z);
                             const double dx = (double)x - (double)px, dy = (double)y - (double)py, dz = (double)z - (double)pz;
-                            const double dn = sqrt(dx * dx + dy * dy + dz * dz);
-                            bmag = sqrt((double)bv.x * bv.x + (double)bv.y * bv.y + (double)bv.z * bv.z);
-                            // radiation propagates towards the observer: against the tracing direction
-                            const double c = -((double)bv.x * dx + (double)bv.y * dy + (double)bv.z * dz) / (bmag * dn);
-                            th = (bmag > 0.0 && dn > 0.0) ? acos(fmin(1.0, fmax(-1.0, c))) * (180.0 / kPi) : 90.0;
+                            const double dn2 = dx * dx + dy * dy + dz * dz;
+                            const double b2 = (double)bv.x * bv.x + (double)bv.y * bv.y + (double)bv.z * bv.z;
+                            bmag = sqrt(b2);
+                            if (b2 > 0.0 && dn2 > 0.0) {
+                                // radiation propagates towards the observer: against the tracing direction
+                                const double c = -((double)bv.x * dx + (double)bv.y * dy + (double)bv.z * dz) * rsqrt(b2 * dn2);
+                                cth = fmin(1.0, fmax(-1.0, c));
+                                sth = sqrt(fmax(0.0, 1.0 - cth * cth));
+                            }
                         }
-                        tr.push(fq, make_voxel((double)ds, (double)f.te, (double)f.ne, bmag, th, a.em_flag, a.s_max));
+                        tr.push(fq, make_voxel_cs((double)ds, (double)f.te, (double)f.ne, bmag, cth, sth, a.em_flag, a.s_max));
                     }
                     px = x; py = y; pz = z;
                     first = false;

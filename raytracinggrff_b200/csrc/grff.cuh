@@ -32,7 +32,7 @@ constexpr double kAu = 1.495978707e13;
 constexpr double kSfu = 1e-19;
 
 struct Voxel {
-    double dz, T, ne, B, th, cth, sth;
+    double dz, T, ne, B, cth, sth;   // theta enters through its cosine and sine only
     int smax;
     bool gr_on, ff_on, ok;
 };
@@ -56,25 +56,28 @@ __device__ __forceinline__ DiagOp diag_then(const DiagOp &first, const DiagOp &s
                   fma(first.bR, second.aR, second.bR)};
 }
 
-__device__ __forceinline__ Voxel make_voxel(double dz, double T, double ne, double B, double th_deg,
-                                            int flag, int smax)
+__device__ __forceinline__ Voxel make_voxel_cs(double dz, double T, double ne, double B, double cth, double sth,
+                                               int flag, int smax)
 {
     Voxel v;
     v.dz = dz; v.T = T; v.ne = ne; v.B = B;
-    v.th = th_deg * (kPi / 180.0);
+    v.cth = cth; v.sth = sth;
     v.smax = smax;
     v.gr_on = !(flag & 1);
     v.ff_on = !(flag & 2);
     v.ok = (dz > 0.0) && (T > 0.0) && (ne > 0.0) && (B >= 0.0) && isfinite(dz) && isfinite(T) &&
-           isfinite(ne) && isfinite(B) && isfinite(v.th);
-    v.cth = 1.0; v.sth = 0.0;
-    if (v.ok) {
-        // theta = 90 deg is what every reference call site passes (script/...:495): skip the sincos;
-        // the constants are sin/cos of the double nearest to pi/2
-        if (th_deg == 90.0) { v.sth = 1.0; v.cth = 6.123233995736766e-17; }
-        else sincos(v.th, &v.sth, &v.cth);
-    }
+           isfinite(ne) && isfinite(B) && isfinite(cth);
     return v;
+}
+
+__device__ __forceinline__ Voxel make_voxel(double dz, double T, double ne, double B, double th_deg,
+                                            int flag, int smax)
+{
+    // theta = 90 deg is what every reference call site passes (script/...:495): skip the sincos;
+    // the constants are sin/cos of the double nearest to pi/2
+    double sth = 1.0, cth = 6.123233995736766e-17;
+    if (th_deg != 90.0) sincos(th_deg * (kPi / 180.0), &sth, &cth);
+    return make_voxel_cs(dz, T, ne, B, cth, sth, flag, smax);
 }
 
 // Refractive index, free-free opacity and Kirchhoff source of mode sg (-1 X, +1 O).
@@ -135,12 +138,14 @@ __device__ __forceinline__ void slab_ab(bool prop, double tau, double src, doubl
 // Per-frequency constants hoisted out of the voxel loop.
 struct FreqC {
     double nu, nu2, inv_nu2, ln_nu;
+    double sn;    // kBres * nu: resonant field of harmonic s is sn / s
 };
 
 __device__ __forceinline__ FreqC make_freq(double nu)
 {
     FreqC f;
     f.nu = nu; f.nu2 = nu * nu; f.inv_nu2 = 1.0 / f.nu2; f.ln_nu = log(nu);
+    f.sn = kBres * nu;
     return f;
 }
 
@@ -231,26 +236,31 @@ struct Between {
     bool qt;
 };
 
-__device__ __forceinline__ Between between_voxels(double nu, const Voxel &p, const Voxel &k)
+__device__ __forceinline__ Between between_voxels(const FreqC &f, const Voxel &p, const Voxel &k)
 {
     Between o;
     o.before = diag_identity(); o.after = diag_identity(); o.Q = 1.0;
     o.qt = (p.cth * k.cth < 0.0);
+    const int smax = min(p.smax, k.smax);
+    const double blo = fmin(p.B, k.B), bhi = fmax(p.B, k.B);
+    // a layer needs the resonant field of some harmonic s <= smax inside (blo, bhi): sn/smax < bhi
+    const bool gr = p.gr_on && k.gr_on && (p.B != k.B) && (bhi * (double)smax > f.sn);
+    if (!o.qt && !gr) return o;                      // the common case: nothing happens in between
+    const double nu = f.nu;
+    const double th_p = acos(p.cth), th_k = acos(k.cth);
     const double dzm = 0.5 * (p.dz + k.dz);
     double tqt = 2.0;
     if (o.qt) {
-        tqt = (0.5 * kPi - p.th) / (k.th - p.th);
-        const double g = fabs(k.th - p.th) / dzm;
+        tqt = (0.5 * kPi - th_p) / (th_k - th_p);
+        const double g = fabs(th_k - th_p) / dzm;
         const double nav = 0.5 * (p.ne + k.ne), Bav = 0.5 * (p.B + k.B);
         o.Q = exp(-kCqt * nav * Bav * Bav * Bav / (nu * nu * nu * nu * g));
     }
-    if (p.gr_on && k.gr_on && p.B != k.B) {
-        const int smax = min(p.smax, k.smax);
+    if (gr) {
         const bool up = k.B > p.B;
-        const double blo = fmin(p.B, k.B), bhi = fmax(p.B, k.B);
-        // harmonics whose resonant field lies strictly inside (blo, bhi): s in (kBres nu/bhi, kBres nu/blo);
+        // harmonics whose resonant field lies strictly inside (blo, bhi): s in (sn/bhi, sn/blo);
         // the range is taken one wider than that and the sign test below decides.
-        const double sn = kBres * nu;
+        const double sn = f.sn;
         const double lo_d = floor(sn / bhi), hi_d = (blo > 0.0) ? ceil(sn / blo) : (double)smax;
         const int s_lo = lo_d > 2.0 ? (lo_d < (double)smax ? (int)lo_d : smax + 1) : 2;
         const int s_hi = hi_d < (double)smax ? (int)hi_d : smax;
@@ -260,7 +270,7 @@ __device__ __forceinline__ Between between_voxels(double nu, const Voxel &p, con
             if (!((p.B - Bres) * (k.B - Bres) < 0.0)) continue;
             const double t = (Bres - p.B) / (k.B - p.B);
             const DiagOp g = gr_layer_op(nu, s, p.ne + t * (k.ne - p.ne), p.T + t * (k.T - p.T),
-                                         p.th + t * (k.th - p.th), Bres * dzm / fabs(k.B - p.B));
+                                         th_p + t * (th_k - th_p), Bres * dzm / fabs(k.B - p.B));
             if (t >= tqt) o.after = diag_then(o.after, g);
             else o.before = diag_then(o.before, g);
         }
@@ -347,7 +357,7 @@ __global__ void __launch_bounds__(128) grff_slice_kernel(const SliceArgs a)
             if (v.ok) {
                 if (k > 0) {
                     const Voxel pv = load_voxel(P + (size_t)(k - 1) * 15);
-                    if (pv.ok && pv.B > 0.0 && v.B > 0.0) { bt = between_voxels(nu, pv, v); has_bt = true; }
+                    if (pv.ok && pv.B > 0.0 && v.B > 0.0) { bt = between_voxels(fq, pv, v); has_bt = true; }
                 }
                 op = voxel_op(fq, v);
             }
@@ -408,7 +418,7 @@ struct OnlineTransfer {
     __device__ __forceinline__ void push(const FreqC &f, const Voxel &v)
     {
         if (!v.ok) { have_prev = false; return; }
-        if (have_prev && prev.B > 0.0 && v.B > 0.0) st.apply(between_voxels(f.nu, prev, v));
+        if (have_prev && prev.B > 0.0 && v.B > 0.0) st.apply(between_voxels(f, prev, v));
         st.apply(voxel_op(f, v));
         prev = v;
         have_prev = true;

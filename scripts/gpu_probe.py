@@ -61,6 +61,24 @@ def main():
             _, _, st = ses.render_map(xs, ys, zs, fp, kvec_in_norm=kv, pixel_area_cm2=area)
             t = timeit(lambda: ses.render_map(xs, ys, zs, fp, kvec_in_norm=kv, pixel_area_cm2=area), n=2)
             print(f"C4 fused f={f/1e6:.0f}MHz: {t*1e3:.1f} ms nominal {st['nominal_ray_steps']/t:.3e} active {st['active_ray_steps']/t:.3e} ray-steps/s")
+    if which == "c4freq":
+        c = synthetic.corona_cube(256, 3.0, active_region=True)
+        ses.set_omega_cube(c["omega_pe"], c["x_grid"], c["y_grid"], c["z_grid"])
+        ses.set_field_cubes(c["x_grid"], c["y_grid"], c["z_grid"], c["ne"], c["te"], c["b"], c["bx"], c["by"], c["bz"])
+        xs, ys, zs, kv = synthetic.ray_launch_geometry(512, 1.44, 3.0)
+        area = (2 * 1.44 / 512 * 6.957e10) ** 2
+        freqs = synthetic.log_frequencies(75e6, 8, np.log10(20.0) / 7)
+        for label, kw in (("GR+FF bvec", dict(em_flag=4, use_bvec=True)), ("FF theta90", dict(em_flag=5, use_bvec=False))):
+            tot = 0.0
+            for f in freqs:
+                p = synthetic.frequency_scaled_params(float(f))
+                fp = [(float(f), p["dt"], p["n_steps"], p["record_stride"])]
+                _, _, st = ses.render_map(xs, ys, zs, fp, pixel_area_cm2=area, **kw)
+                ms = ses.ctx.last_kernel_ms
+                tot += ms
+                print(f"{label} f={f/1e6:7.1f} MHz T={p['n_steps']:6d} stride={p['record_stride']}: {ms:7.1f} ms  "
+                      f"active {st['active_ray_steps']/ms/1e6:.2f} G ray-steps/s  ({st['active_ray_steps']/st['nominal_ray_steps']:.2f} active)")
+            print(f"{label} total {tot:.1f} ms")
     if which == "tile":
         c = synthetic.corona_cube(256, 3.0)
         ses.set_omega_cube(c["omega_pe"], c["x_grid"], c["y_grid"], c["z_grid"])

@@ -330,3 +330,60 @@ def test_render_map_multi_frequency_and_orders(oracle, session):
     rev = {k: v[::-1].copy() for k, v in smp.items()}
     tb_ref, vi_ref, _ = oracle.emission_from_samples(rev, N_pix, X_fov, p["freq_hz"])
     _cmp_maps(tb_r[0].reshape(N_pix, N_pix, 1), vi_r[0].reshape(N_pix, N_pix, 1), tb_ref, vi_ref)
+
+
+def test_render_map_theta_from_bvec_gr_on(oracle, session):
+    """GR+FF with theta from B.t along the ray (beyond the reference, which fixes theta = 90 deg):
+    the oracle is fed Parms built in numpy from the oracle's own paths — B vector sampled with the
+    sampler's float32 arithmetic, theta = acos(-B.d/|B||d|) with d the step between consecutive valid
+    float32 samples, |B| = |B vector|, flag 4 (GR and FF on), s_max 30."""
+    c = synthetic.corona_cube(64, 3.0, active_region=True)
+    session.set_omega_cube(c["omega_pe"], c["x_grid"], c["y_grid"], c["z_grid"])
+    session.set_field_cubes(c["x_grid"], c["y_grid"], c["z_grid"], c["ne"], c["te"], c["b"], c["bx"], c["by"], c["bz"])
+    N_pix, X_fov, freq = 12, 1.2, 1.0e9
+    p = synthetic.frequency_scaled_params(freq)
+    p["record_stride"] = 4
+    xs, ys, zs, kv = synthetic.ray_launch_geometry(N_pix, X_fov, 3.0)
+    area = (2 * X_fov / N_pix * 6.957e10) ** 2
+    tb, vi, _ = session.render_map(xs, ys, zs, [dict(freq_hz=freq, **p)], kvec_in_norm=kv, pixel_area_cm2=area,
+                                   em_flag=4, s_max=30, use_bvec=True)
+    r, cs = oracle.ray_trace(c["omega_pe"], c["x_grid"], c["y_grid"], c["z_grid"], freq, xs, ys, zs, kv, p["dt"],
+                             p["n_steps"], p["record_stride"], True, perturb_ratio=2)
+    ray_start = np.column_stack([xs, ys, zs])
+    g3 = (c["x_grid"], c["y_grid"], c["z_grid"])
+    smp = oracle.sample_model_with_rays_cpu(*g3, c["ne"], c["te"], c["b"], r, np.array(cs), ray_start, 6.957e10)
+    bv = oracle.sample_model_with_rays_cpu(*g3, c["bx"], c["by"], c["bz"], r, np.array(cs), ray_start, 6.957e10,
+                                           fill_ne=0.0, fill_te=0.0, fill_b=0.0)
+    pos = r.astype(np.float32).astype(np.float64)
+    start32 = ray_start.astype(np.float32).astype(np.float64)
+    tb_ref = np.zeros(N_pix * N_pix)
+    vi_ref = np.zeros(N_pix * N_pix)
+    n_gr = 0
+    for q in range(N_pix * N_pix):
+        valid = smp["valid_mask"][:, q]
+        idx = np.flatnonzero(valid)
+        if idx.size == 0:
+            continue
+        prev = np.vstack([start32[q][None], pos[idx[:-1], q]])
+        d = pos[idx, q] - prev
+        B = np.stack([bv["ne"][idx, q], bv["te"][idx, q], bv["b"][idx, q]], axis=1).astype(np.float64)
+        b2 = (B * B).sum(1)
+        dn2 = (d * d).sum(1)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            cth = np.clip(-(B * d).sum(1) / np.sqrt(b2 * dn2), -1.0, 1.0)
+        cth = np.where((b2 > 0) & (dn2 > 0), cth, 6.123233995736766e-17)
+        P = np.zeros((15, idx.size), order="F")
+        P[0] = smp["ds"][idx, q]; P[1] = smp["te"][idx, q]; P[2] = smp["ne"][idx, q]; P[3] = np.sqrt(b2)
+        P[4] = np.degrees(np.arccos(cth)); P[6] = 4; P[7] = 30
+        RL = np.zeros((7, 1), order="F")
+        assert oracle.get_mw(np.array([idx.size, 1, 0, 0, 0], dtype=np.int32), np.array([area, freq, 0.0]), P,
+                             None, None, None, RL) == 0
+        conv = (1e-19 * 2.998e10 ** 2 / (2.0 * 1.38065e-16 * (RL[0, 0] * 1e9) ** 2) / area) * 1.49599e13 ** 2
+        tb_ref[q] = (RL[5, 0] + RL[6, 0]) * conv
+        vi_ref[q] = (RL[5, 0] - RL[6, 0]) / (RL[5, 0] + RL[6, 0] + 1e-30)
+        bres = 3.57238675287821e-07 * freq / np.arange(2, 31)
+        n_gr += int(np.any((P[3].min() < bres) & (bres < P[3].max())))
+    assert n_gr > 0                      # the active region puts gyroresonance layers on some rays
+    assert np.abs(vi_ref).max() > 1e-3   # and polarises the map
+    _cmp_maps(tb[0].reshape(N_pix, N_pix, 1), vi[0].reshape(N_pix, N_pix, 1), tb_ref.reshape(N_pix, N_pix, 1),
+              vi_ref.reshape(N_pix, N_pix, 1))
