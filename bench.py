@@ -194,7 +194,9 @@ def config_dict(w, args):
         "per_freq": [[p["freq_hz"], p["dt"], p["n_steps"], p["record_stride"]] for p in w["freq_params"]],
         "sharding": "rows interleaved over ranks, cube replicated, NCCL all-gather of the image",
         "l2": "cubes (2 x 268 MB float4 at 256^3) exceed the 126 MB L2; no flush between steps",
-        "precision": "FP64 ray state and transfer, FP32 cube storage / trilinear arithmetic",
+        "precision": "FP64 ray state and transfer, FP32 cube storage and cell-relative RHS",
+        "cross_sections": "pencil rays traced on recorded steps only (the reference computes S at every step but "
+                          "outputs only recorded steps, build_rays.py:241-244); RTGRFF_CS_EVERY_STEP=1 restores it",
     }
 
 
@@ -297,26 +299,31 @@ def main():
     launches0 = ses.ctx.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kernel_ms = []
-    active_local = 0
+    active_local = pencil_local = samples_local = 0
     ev0.record()
     for _ in range(args.steps):
         img = render()
         kernel_ms.append(stats_box["kernel_ms"])
         active_local = stats_box["active_ray_steps"]
+        pencil_local = stats_box["pencil_steps"]
+        samples_local = stats_box["valid_samples"]
     ev1.record()
     barrier()
     clk = clocks.stop()
     launches = ses.ctx.launch_count - launches0
     ms = ev0.elapsed_time(ev1)
-    t = torch.tensor([ms, float(active_local), float(np.mean(kernel_ms))], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, float(active_local), float(np.mean(kernel_ms)), float(pencil_local), float(samples_local)],
+                     dtype=torch.float64, device=dev)
     if world > 1:
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         ms, active_total, kernel_ms_max = float(tmax[0]), float(tsum[1]), float(tmax[2])
+        pencil_total, samples_total = float(tsum[3]), float(tsum[4])
     else:
         active_total, kernel_ms_max = float(active_local), float(t[2])
+        pencil_total, samples_total = float(pencil_local), float(samples_local)
     ms_per_step = ms / args.steps
     value = nominal_total / (ms_per_step * 1e-3)
 
@@ -356,7 +363,12 @@ def main():
             traffic = json.load(open(ROOT / "profiles" / "roofline_traffic.json")).get("render_map_kernel_dram_bytes_per_launch")
         except Exception:
             pass
-        alg_bytes = active_total / world * BYTES_PER_RAY_STEP_CS      # per launch (one launch per rank per step)
+        # algorithmic bytes per launch (one launch per rank per step), SURVEY 8d per-unit figures x the units
+        # actually processed: 512 B per central RK4 step, 1024 B per step on which the two pencil rays are
+        # traced (recorded steps only: the reference discards the cross-section ratio of the others),
+        # 2 x 128 B of field/B-vector corners + 16 B of state per valid sample
+        alg_bytes = (active_total * BYTES_PER_RAY_STEP_NOCS + pencil_total * (BYTES_PER_RAY_STEP_CS - BYTES_PER_RAY_STEP_NOCS)
+                     + samples_total * (2 * 128 + 16)) / world
         achieved = alg_bytes / (kernel_ms_max * 1e-3) / 1e9
         line = {
             "metric": "ray_steps_per_s", "value": value, "unit": "ray-steps/s", "n_gpus": world, "steps": args.steps,
@@ -365,6 +377,7 @@ def main():
             "full_map_wall_s": ms_per_step * 1e-3,
             "nominal_ray_steps_per_step": nominal_total, "active_ray_steps_per_step": active_total,
             "active_ray_steps_per_s": active_total / (ms_per_step * 1e-3),
+            "pencil_steps_per_step": pencil_total, "valid_samples_per_step": samples_total,
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "ray-steps/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "full_map_wall_s": e2e_t},
@@ -372,9 +385,9 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "render_map_kernel", "kernel_ms": kernel_ms_max,
                          "peak_source": peak_src,
-                         "note": "achieved = active ray-steps x 1536 B (SURVEY 8d) / kernel time; the gathers are "
-                                 "served by L1/L2 (DRAM traffic ~ cube size), so the algorithmic rate can exceed the "
-                                 "HBM copy peak; see DESIGN.md for the L1/FP64 pipe ceilings"},
+                         "note": "achieved = (512 B x active central steps + 1024 B x pencil steps + 272 B x valid "
+                                 "samples) / kernel time; the gathers are served by registers/L1 (DRAM traffic ~ cube "
+                                 "size), so the algorithmic rate can exceed the HBM copy peak; see DESIGN.md 4.1"},
         }
         if not args.no_cpu_baseline:
             from oracle import oracle

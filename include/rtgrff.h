@@ -160,7 +160,8 @@ typedef struct {
  *  Rays: x_start,y_start,z_start host float64 (n_rays), direction (0,0,-1) unless kvec != NULL.
  *  use_bvec: 0 -> theta=90 deg (reference behaviour); 1 -> theta from B.t along the ray (needs bx,by,bz).
  *  tb, vi: float64 (n_freq, n_rays); host, or device pointers when out_on_device != 0.
- *  stats (optional, host int64[2]): {nominal ray-steps, active ray-steps}.
+ *  stats (optional, host int64[4]): {nominal ray-steps, active ray-steps (the ray still moved),
+ *  steps on which the two cross-section rays were traced, valid samples handed to the transfer}.
  */
 int rtgrff_render_map(rtgrff_ctx *ctx, int64_t n_rays, const double *x_start, const double *y_start,
                       const double *z_start, const double *kvec, int n_freq,

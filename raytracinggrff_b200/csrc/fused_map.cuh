@@ -36,7 +36,7 @@ struct MapArgs {
     float r_sun_cm, fill_ne, fill_te, fill_b;
     int em_flag, s_max, use_bvec, order, cs_every_step;
     double *tb, *vi;                     // [freq][ray]
-    unsigned long long *active_steps;
+    unsigned long long *active_steps;    // [0] active central steps, [1] steps with the pencil traced, [2] valid samples
 };
 
 // Transfer accumulated from the observer outwards (RTGRFF_ORDER_REVERSED): the records arrive
@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_MINB) render_map_kernel(const Map
     bool alive = has_ray;
     double s_step = CS ? 0.0 : 1.0;
     unsigned long long moved_steps = 0;
+    unsigned int pencil_steps = 0, n_samples = 0;
     int64_t next_rec = 0;
 
     typename std::conditional<ORDER == RTGRFF_ORDER_RECORD, RecordTransfer<NEED_BETWEEN>,
@@ -151,6 +152,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_MINB) render_map_kernel(const Map
             const bool want_s = CS && (i == next_rec || a.cs_every_step);
             alive = advance_ray<CS, MODE>(C, K, cache, s, fp.dt, a.perturb_ratio, want_s, s_step);
             moved_steps += alive ? 1ull : 0ull;
+            pencil_steps += (want_s && alive) ? 1u : 0u;
         }
         if (i == next_rec) {
             next_rec += fp.stride;
@@ -158,6 +160,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_MINB) render_map_kernel(const Map
                 // --- sampler (float32, gpu_raytrace.py:642-650) ---
                 const float x = (float)s.rx, y = (float)s.ry, z = (float)s.rz, sv = (float)s_step;
                 if (sample_valid(x, y, z, sv)) {
+                    ++n_samples;
                     const FieldSample f = sample_fields(a.fcube, a.fg, x, y, z, a.fill_ne, a.fill_te, a.fill_b);
                     const float dist = first ? dist_first_np(x, y, z, px, py, pz) : dist_np(x, y, z, px, py, pz);
                     const float ds = __fmul_rn(dist, a.r_sun_cm);
@@ -196,8 +199,17 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_MINB) render_map_kernel(const Map
         a.vi[(size_t)fi * a.n_rays + ray] = vi;
     }
     if (a.active_steps) {
-        for (int off = 16; off > 0; off >>= 1) moved_steps += __shfl_down_sync(0xffffffffu, moved_steps, off);
-        if ((threadIdx.x & 31) == 0 && moved_steps) atomicAdd(a.active_steps, moved_steps);
+        unsigned long long ps = pencil_steps, ns = n_samples;
+        for (int off = 16; off > 0; off >>= 1) {
+            moved_steps += __shfl_down_sync(0xffffffffu, moved_steps, off);
+            ps += __shfl_down_sync(0xffffffffu, ps, off);
+            ns += __shfl_down_sync(0xffffffffu, ns, off);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            if (moved_steps) atomicAdd(a.active_steps, moved_steps);
+            if (ps) atomicAdd(a.active_steps + 1, ps);
+            if (ns) atomicAdd(a.active_steps + 2, ns);
+        }
     }
 }
 

@@ -97,9 +97,11 @@ __device__ __forceinline__ Deriv32 rhs32(const RayCube &C, int bi, int bj, int b
 #undef RT_HI
     const float w = wg.x;
     const float om2 = fmaf(w, w, fmaf(kx, kx, fmaf(ky, ky, kz * kz)));
-    // valid = isfinite(omega_pe) & isfinite(omega) & (omega > 0)   (build_rays.py:169)
-    if (!(om2 > 0.0f) || !(om2 < INFINITY) || !(fabsf(w) < INFINITY)) return d;
-    const float inv_om = rsqrtf(om2);
+    // valid = isfinite(omega_pe) & isfinite(omega) & (omega > 0)   (build_rays.py:169); a non-finite
+    // omega_pe or k makes omega^2 non-finite, so one range test on omega^2 covers all three
+    if (!(om2 > 0.0f) || !(om2 < INFINITY)) return d;
+    float inv_om;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv_om) : "f"(om2));   // MUFU.RSQ, 2 ulp; omega^2 ~ 1e17
     const float a = w * inv_om;
     d.vx = kx * inv_om; d.vy = ky * inv_om; d.vz = kz * inv_om;
     d.gx = a * wg.y; d.gy = a * gg.x; d.gz = a * gg.y;
@@ -192,7 +194,11 @@ __device__ __forceinline__ void step32_body(const RayCube &C, const StepConst &K
         const float eps = K.perturb * nrd;
         float d1x = 0.f, d1y = 0.f, d1z = 0.f, d2x = 0.f, d2y = 0.f, d2z = 0.f;
         // the two pencil rays share one code body (keeps the kernel inside the instruction cache)
+#ifdef RT_PENCIL_UNROLL
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
         for (int q = 0; q < 2; ++q) {
             const float ex = eps * (q ? e2x : e1x), ey = eps * (q ? e2y : e1y), ez = eps * (q ? e2z : e1z);
             const RkSum a = rk4_32<EDGE>(C, K, bi, bj, bk, base_off, cache, fmaf(ex, K.ix, px), fmaf(ey, K.iy, py),

@@ -499,7 +499,7 @@ int rtgrff_render_map(rtgrff_ctx *c, int64_t n_rays, const double *x_start, cons
     if (n_rays < 0 || n_freq <= 0 || n_freq > 65535 || !freqs || !tb || !vi) return fail(RTGRFF_EINVAL, "bad arguments");
     if (voxel_order != RTGRFF_ORDER_RECORD && voxel_order != RTGRFF_ORDER_REVERSED) return fail(RTGRFF_EINVAL, "bad voxel_order");
     if (n_rays > 0 && (!x_start || !y_start || !z_start)) return fail(RTGRFF_EINVAL, "null start arrays");
-    if (stats) stats[0] = stats[1] = 0;
+    if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
     if (n_rays == 0) return RTGRFF_OK;
     std::vector<FreqDev> fd(n_freq);
     int64_t nominal = 0;
@@ -575,10 +575,10 @@ int rtgrff_render_map(rtgrff_ctx *c, int64_t n_rays, const double *x_start, cons
         RT_TRY(d2h(c, tb, dtb, (size_t)n_freq * nb));
         RT_TRY(d2h(c, vi, dvi, (size_t)n_freq * nb));
     }
-    unsigned long long act = 0;
-    RT_TRY(d2h(c, &act, c->counters.p, sizeof(act)));
+    unsigned long long act[3] = {0, 0, 0};
+    RT_TRY(d2h(c, act, c->counters.p, sizeof(act)));
     RT_CUDA(cudaStreamSynchronize(c->stream));
-    if (stats) { stats[0] = nominal; stats[1] = (int64_t)act; }
+    if (stats) { stats[0] = nominal; stats[1] = (int64_t)act[0]; stats[2] = (int64_t)act[1]; stats[3] = (int64_t)act[2]; }
     return RTGRFF_OK;
 }
 

@@ -179,7 +179,7 @@ class RaySession:
             if isinstance(p, dict):
                 p = (p["freq_hz"], p["dt"], p["n_steps"], p["record_stride"])
             arr[i] = FreqParams(float(p[0]), float(p[1]), int(p[2]), int(p[3]))
-        stats = (c_int64 * 2)()
+        stats = (c_int64 * 4)()
         if out_device_ptrs is None:
             tb = np.empty((nf, n_rays), dtype=np.float64)
             vi = np.empty_like(tb)
@@ -192,4 +192,5 @@ class RaySession:
                                           int(bool(trace_crosssections)), float(perturb_ratio), float(pixel_area_cm2),
                                           float(r_sun_cm), int(em_flag), int(s_max), int(bool(use_bvec)),
                                           int(voxel_order), ptb, pvi, on_dev, stats))
-        return tb, vi, {"nominal_ray_steps": int(stats[0]), "active_ray_steps": int(stats[1])}
+        return tb, vi, {"nominal_ray_steps": int(stats[0]), "active_ray_steps": int(stats[1]),
+                        "pencil_steps": int(stats[2]), "valid_samples": int(stats[3])}
