@@ -216,6 +216,12 @@ def main():
     if args.impl == "reference":
         return run_reference(args, w)
 
+    # keep stdout clean for the single JSON line: anything libraries print there (NCCL's version banner
+    # among others) goes to stderr until the result is ready
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     from raytracinggrff_b200 import RaySession, _lib
@@ -398,7 +404,9 @@ def main():
                 "value": n / tcpu, "unit": "ray-steps/s", "cores": os.cpu_count(), "kind": "port",
                 "sample": f"{n_rays} rays (every {args.cpu_sample_stride}th pixel in x and y) x {nf} freqs, full n_steps; "
                           f"oracle trace + sampler + GET_MW (theta=90 free-free packing), {tcpu:.1f} s"}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

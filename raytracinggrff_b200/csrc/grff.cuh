@@ -203,8 +203,9 @@ __device__ __forceinline__ DiagOp voxel_op(const FreqC &f, const Voxel &v)
     return (v.cth >= 0.0) ? DiagOp{aO, aX, bO, bX} : DiagOp{aX, aO, bX, bO};
 }
 
-// One gyroresonance layer nu = s nu_B at interpolated plasma parameters.
-__device__ __forceinline__ DiagOp gr_layer_op(double nu, int s, double ne, double T, double th, double LB)
+// One gyroresonance layer nu = s nu_B at interpolated plasma parameters.  Rare and heavy (lgamma,
+// log, exp, sincos): kept out of line so the hot loops stay small.
+__device__ __noinline__ DiagOp gr_layer_op(double nu, int s, double ne, double T, double th, double LB)
 {
     double sth, cth;
     sincos(th, &sth, &cth);
