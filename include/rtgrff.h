@@ -75,6 +75,31 @@ int rtgrff_set_field_cubes(rtgrff_ctx *ctx, const float *ne, const float *te, co
                            const float *bx, const float *by, const float *bz,
                            int nx, int ny, int nz, const double geom[12]);
 
+/*
+ * Resample one variable of a spherical (phi, latitude, r) model onto the xyz cube and keep it on
+ * the device in `slot` (0 rho/n_e, 1 te, 2 br, 3 bt, 4 bp); `out` (host float64 (nx,ny,nz), may be
+ * NULL) receives a copy.  Replaces resample_to_xyz_cube (build_rays.py:69-125) and
+ * resample_var_to_cube (script/resample_with_ray_tracing.py:110-151): cart_to_sph(x,-z,y,phi0),
+ * linear interpolation with periodic phi (psipy's sample_at_coords), r < r_min or outside the mesh
+ * -> NaN -> `fill` when fill_nonfinite.  data: host float32 (np,nt,nr) C-order; phi, lat, r: host
+ * float64 node coordinates (rad, rad, R_sun), ascending; value = sample * scale.  x_grid, y_grid,
+ * z_grid: host float64 cube nodes (used as they are, so a node on the rotation axis stays on it).
+ */
+int rtgrff_resample_spherical(rtgrff_ctx *ctx, int slot, const float *data, const double *phi,
+                              const double *lat, const double *r, int np, int nt, int nr,
+                              const double *x_grid, const double *y_grid, const double *z_grid, int nx,
+                              int ny, int nz, const double geom[12], double phi0_offset_deg, double r_min,
+                              double scale, double fill, int fill_nonfinite, double *out);
+
+/*
+ * Build the device cubes of the ray path from the five resampled slots with the reference's rules
+ * (script/resample_with_ray_tracing.py:269-293): omega_pe = 2 pi 8.93e3 sqrt(max(rho,0)) (NaN -> 0)
+ * and its numpy.gradient, n_e = max(rho,0), T NaN -> 1e4, |B| = sqrt(br^2+bt^2+bp^2); with
+ * want_bvec also the Cartesian B vector (for theta from B.t).  Equivalent to rtgrff_set_omega_cube
+ * + rtgrff_set_field_cubes without the cubes ever visiting the host.
+ */
+int rtgrff_compose_cubes(rtgrff_ctx *ctx, int want_bvec);
+
 /* How the cross-section ratio S is recorded. */
 #define RTGRFF_S_PER_STEP 0     /* CPU reference: ratio of the recorded step only (build_rays.py:239-244) */
 #define RTGRFF_S_CUMULATIVE 1   /* CUDA reference: running product since the start (gpu_raytrace.py:398-408) */

@@ -106,6 +106,13 @@ struct rtgrff_ctx {
     rtgrff::DevBuf smp_ne, smp_te, smp_b, smp_ds, smp_s, smp_valid;
     int64_t smp_n = 0, smp_rays = 0;
 
+    // cubes resampled from a spherical model (rho, te, br, bt, bp as float64) before composition
+    rtgrff::DevBuf slot[5];
+    bool slot_set[5] = {false, false, false, false, false};
+    int slot_nx = 0, slot_ny = 0, slot_nz = 0;
+    double slot_geom[12] = {0};
+    rtgrff::DevBuf slot_grids;       // x, y, z node coordinates of the slots' cube
+
     // scratch
     rtgrff::DevBuf in0, in1, in2, in3, out0, out1, out2, out3, out4, out5, stage, counters;
 };

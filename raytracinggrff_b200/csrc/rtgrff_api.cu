@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "cube_builder.cuh"
 #include "fused_map.cuh"
 #include "grff.cuh"
 #include "los_sampler.cuh"
@@ -179,6 +180,8 @@ int rtgrff_ctx_destroy(rtgrff_ctx *c)
                       &c->smp_ds, &c->smp_s, &c->smp_valid, &c->in0, &c->in1, &c->in2, &c->in3, &c->out0, &c->out1,
                       &c->out2, &c->out3, &c->out4, &c->out5, &c->stage, &c->counters};
     for (DevBuf *b : bufs) b->release();
+    for (DevBuf &b : c->slot) b.release();
+    c->slot_grids.release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -262,6 +265,99 @@ int rtgrff_set_field_cubes(rtgrff_ctx *c, const float *ne, const float *te, cons
     c->has_fcube = true;
     c->has_bvec = bvec;
     RT_CUDA(cudaStreamSynchronize(c->stream));
+    return RTGRFF_OK;
+}
+
+int rtgrff_resample_spherical(rtgrff_ctx *c, int slot, const float *data, const double *phi, const double *lat,
+                              const double *r, int np, int nt, int nr, const double *x_grid, const double *y_grid,
+                              const double *z_grid, int nx, int ny, int nz, const double geom[12],
+                              double phi0_offset_deg, double r_min, double scale, double fill, int fill_nonfinite,
+                              double *out)
+{
+    RT_TRY(use(c));
+    if (slot < 0 || slot > 4) return fail(RTGRFF_EINVAL, "slot %d out of range 0..4", slot);
+    if (!data || !phi || !lat || !r || !geom || !x_grid || !y_grid || !z_grid) return fail(RTGRFF_EINVAL, "null argument");
+    if (np < 2 || nt < 2 || nr < 2) return fail(RTGRFF_EINVAL, "spherical mesh needs >= 2 nodes per axis");
+    GridGeom g;
+    RT_TRY(geom_from(geom, nx, ny, nz, g));
+    for (int i = 1; i < np; ++i) if (!(phi[i] > phi[i - 1])) return fail(RTGRFF_EINVAL, "phi nodes must ascend");
+    for (int i = 1; i < nt; ++i) if (!(lat[i] > lat[i - 1])) return fail(RTGRFF_EINVAL, "latitude nodes must ascend");
+    for (int i = 1; i < nr; ++i) if (!(r[i] > r[i - 1])) return fail(RTGRFF_EINVAL, "radius nodes must ascend");
+    if (c->slot_nx && (c->slot_nx != nx || c->slot_ny != ny || c->slot_nz != nz))
+        for (bool &b : c->slot_set) b = false;           // a new cube shape invalidates the other slots
+    const size_t nvox = (size_t)nx * ny * nz, nd = (size_t)np * nt * nr;
+    RT_TRY(h2d(c, c->in0, data, nd * sizeof(float)));
+    RT_TRY(c->in1.reserve((size_t)(np + nt + nr) * sizeof(double)));
+    double *ax = c->in1.as<double>();
+    RT_CUDA(cudaMemcpyAsync(ax, phi, np * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    RT_CUDA(cudaMemcpyAsync(ax + np, lat, nt * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    RT_CUDA(cudaMemcpyAsync(ax + np + nt, r, nr * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    RT_TRY(c->slot[slot].reserve(nvox * sizeof(double)));
+    RT_TRY(c->slot_grids.reserve((size_t)(nx + ny + nz) * sizeof(double)));
+    double *gx = c->slot_grids.as<double>();
+    RT_CUDA(cudaMemcpyAsync(gx, x_grid, nx * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    RT_CUDA(cudaMemcpyAsync(gx + nx, y_grid, ny * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    RT_CUDA(cudaMemcpyAsync(gx + nx + ny, z_grid, nz * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    ResampleArgs a;
+    a.mesh.data = c->in0.as<float>();
+    a.mesh.phi = ax; a.mesh.lat = ax + np; a.mesh.r = ax + np + nt;
+    a.mesh.np = np; a.mesh.nt = nt; a.mesh.nr = nr;
+    a.nx = nx; a.ny = ny; a.nz = nz;
+    a.xg = gx; a.yg = gx + nx; a.zg = gx + nx + ny;
+    a.phi0_offset_rad = phi0_offset_deg * M_PI / 180.0;
+    a.r_min = r_min; a.scale = scale; a.fill = fill; a.fill_nonfinite = fill_nonfinite;
+    a.out = c->slot[slot].as<double>();
+    unsigned int blocks = blocks_for((int64_t)nvox, 256);
+    const unsigned int cap = (unsigned int)c->sm_count * 32;
+    if (blocks > cap) blocks = cap;
+    RT_CUDA(cudaEventRecord(c->ev0, c->stream));
+    resample_spherical_kernel<<<blocks, 256, 0, c->stream>>>(a);
+    RT_TRY(launched(c, "resample_spherical_kernel"));
+    RT_CUDA(cudaEventRecord(c->ev1, c->stream));
+    c->ev_valid = true;
+    if (out) RT_TRY(d2h(c, out, c->slot[slot].p, nvox * sizeof(double)));
+    RT_CUDA(cudaStreamSynchronize(c->stream));
+    c->slot_set[slot] = true;
+    c->slot_nx = nx; c->slot_ny = ny; c->slot_nz = nz;
+    memcpy(c->slot_geom, geom, sizeof(c->slot_geom));
+    return RTGRFF_OK;
+}
+
+int rtgrff_compose_cubes(rtgrff_ctx *c, int want_bvec)
+{
+    RT_TRY(use(c));
+    for (int s = 0; s < 5; ++s)
+        if (!c->slot_set[s]) return fail(RTGRFF_ENOCUBE, "spherical slot %d (0 rho, 1 te, 2 br, 3 bt, 4 bp) is not set", s);
+    const int nx = c->slot_nx, ny = c->slot_ny, nz = c->slot_nz;
+    const double *geom = c->slot_geom;
+    GridGeom g;
+    RT_TRY(geom_from(geom, nx, ny, nz, g));
+    const size_t nvox = (size_t)nx * ny * nz;
+    RT_TRY(c->stage.reserve(nvox * sizeof(double)));
+    RT_TRY(c->fcube.reserve(nvox * sizeof(float4)));
+    if (want_bvec) RT_TRY(c->bcube.reserve(nvox * sizeof(float4)));
+    RT_TRY(c->wcube.reserve(nvox * sizeof(float4)));
+    ComposeArgs a;
+    a.ne = c->slot[0].as<double>(); a.te = c->slot[1].as<double>();
+    a.br = c->slot[2].as<double>(); a.bt = c->slot[3].as<double>(); a.bp = c->slot[4].as<double>();
+    a.nx = nx; a.ny = ny; a.nz = nz;
+    a.xg = c->slot_grids.as<double>(); a.yg = a.xg + nx; a.zg = a.yg + ny;
+    a.omega_pe = c->stage.as<double>();
+    a.fcube = c->fcube.as<float4>();
+    a.bcube = want_bvec ? c->bcube.as<float4>() : nullptr;
+    unsigned int blocks = blocks_for((int64_t)nvox, 256);
+    compose_cubes_kernel<<<blocks, 256, 0, c->stream>>>(a);
+    RT_TRY(launched(c, "compose_cubes_kernel"));
+    build_ray_cube_kernel<<<blocks, 256, 0, c->stream>>>(c->stage.as<double>(), c->wcube.as<float4>(), nx, ny, nz,
+                                                          geom[3], geom[7], geom[11]);
+    RT_TRY(launched(c, "build_ray_cube_kernel"));
+    RT_CUDA(cudaStreamSynchronize(c->stream));
+    c->wgeom = g; c->fgeom = g;
+    GridGeomF &f = c->fgeomf;
+    f.nx = nx; f.ny = ny; f.nz = nz;
+    f.x0 = (float)geom[0]; f.y0 = (float)geom[4]; f.z0 = (float)geom[8];
+    f.idx = (float)(1.0 / geom[1]); f.idy = (float)(1.0 / geom[5]); f.idz = (float)(1.0 / geom[9]);
+    c->has_wcube = true; c->has_fcube = true; c->has_bvec = want_bvec != 0;
     return RTGRFF_OK;
 }
 

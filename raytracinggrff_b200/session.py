@@ -59,6 +59,12 @@ class RaySession:
                                                ptr(vec[0], c_float), ptr(vec[1], c_float), ptr(vec[2], c_float),
                                                *shape, ptr(geom, c_double)))
 
+    def set_model_from_spherical(self, model, x_grid, y_grid, z_grid, phi0_offset=0.0, want_bvec=False):
+        """Cubes straight from a spherical (phi, latitude, r) model, never visiting the host
+        (cubes.set_model_from_spherical; script/resample_with_ray_tracing.py:263-293)."""
+        from . import cubes
+        cubes.set_model_from_spherical(self, model, x_grid, y_grid, z_grid, phi0_offset, want_bvec)
+
     # -- integrator ----------------------------------------------------------------------------
     def trace(self, freq_hz, x_start, y_start, z_start, kvec_in_norm, dt, n_steps, record_stride=10,
               trace_crosssections=False, perturb_ratio=2.0, s_mode=_lib.S_PER_STEP, fetch=True):

@@ -169,3 +169,68 @@ def tile_order(n_x, n_y, tile_w=8, tile_h=4):
     tiles_x = (n_x + tile_w - 1) // tile_w
     key = ((i // tile_h) * tiles_x + (j // tile_w)) * (tile_w * tile_h) + (i % tile_h) * tile_w + (j % tile_w)
     return np.argsort(key.ravel(), kind="stable")
+
+
+def spherical_corona(n_r=80, n_lat=60, n_phi=90, r_max=6.0, active_region=False, b0=2.0, stagger=True):
+    """The analytic corona of `corona_cube` sampled on a MAS-like spherical mesh: non-uniform in r
+    (geometric stretch away from the surface) and in latitude (finer near the equator), uniform in
+    longitude, with br / bt / bp on half-cell staggered meshes like MAS.  Values are stored in
+    physical units (scale 1).  Model frame as in build_rays.py:93: cube (x, y, z) = model
+    (x, z, -y); the solar axis is the model's z."""
+    from .cubes import SphericalVariable
+
+    def mesh(shift_r=False, shift_t=False, shift_p=False):
+        xi = np.linspace(0.0, 1.0, n_r)
+        r = 1.0 + (r_max - 1.0) * (np.expm1(3.0 * xi) / np.expm1(3.0))
+        r[0] = 0.9995
+        if shift_r:
+            r = np.concatenate([[0.999], 0.5 * (r[1:] + r[:-1]), [r_max * 1.001]])
+        eta = np.linspace(-1.0, 1.0, n_lat)
+        lat = 0.5 * np.pi * (0.7 * eta + 0.3 * eta ** 3)
+        if shift_t:
+            lat = np.concatenate([[lat[0]], 0.5 * (lat[1:] + lat[:-1]), [lat[-1]]])
+        phi = np.linspace(0.0, 2 * np.pi, n_phi, endpoint=False)
+        if shift_p:
+            phi = phi + 0.5 * (phi[1] - phi[0])
+        return phi, lat, r
+
+    def fields(phi, lat, r):
+        P, T, R = np.meshgrid(phi, lat, r, indexing="ij")
+        zc = R * np.sin(T)                      # model z (solar axis)
+        xm = R * np.cos(T) * np.cos(P)
+        ym = R * np.cos(T) * np.sin(P)
+        cx, cy, cz = xm, zc, -ym                # cube frame
+        rs = np.maximum(R, 1e-3)
+        latd = np.degrees(np.arcsin(np.clip(cy / rs, -1.0, 1.0)))
+        ne = 4.2e4 * 10.0 ** (4.32 / rs) * (1.0 + 0.5 * np.exp(-(latd / 15.0) ** 2))
+        te = 1.0e6 + 0.4e6 * np.tanh(rs - 1.0)
+        mr = cy / rs
+        f = b0 / rs ** 3
+        bx, by, bz = f * (3 * mr * cx / rs), f * (3 * mr * cy / rs - 1.0), f * (3 * mr * cz / rs)
+        if active_region:
+            c = np.array([0.30, 0.20, np.sqrt(1.0 - 0.30 ** 2 - 0.20 ** 2)]) * 0.95
+            m = c / np.linalg.norm(c)
+            d = 0.05
+            px, py, pz = cx - c[0], cy - c[1], cz - c[2]
+            pr = np.maximum(np.sqrt(px * px + py * py + pz * pz), 0.25 * d)
+            md = (m[0] * px + m[1] * py + m[2] * pz) / pr
+            fa = 300.0 * (d / pr) ** 3
+            bx = bx + fa * (3 * md * px / pr - m[0]); by = by + fa * (3 * md * py / pr - m[1]); bz = bz + fa * (3 * md * pz / pr - m[2])
+        # cube-frame vector -> model frame -> (br, bt, bp) with theta the colatitude from the model z
+        vx, vy, vz = bx, -bz, by
+        st, ct = np.cos(T), np.sin(T)           # colatitude: sin(theta) = cos(lat)
+        cp, sp = np.cos(P), np.sin(P)
+        br = vx * st * cp + vy * st * sp + vz * ct
+        bt = vx * ct * cp + vy * ct * sp - vz * st
+        bp = -vx * sp + vy * cp
+        return ne, te, br, bt, bp
+
+    out = {}
+    phi, lat, r = mesh()
+    ne, te, _, _, _ = fields(phi, lat, r)
+    out["rho"] = SphericalVariable(ne.astype(np.float32), phi, lat, r)
+    out["te"] = SphericalVariable(te.astype(np.float32), phi, lat, r)
+    for name, idx, sh in (("br", 2, dict(shift_r=stagger)), ("bt", 3, dict(shift_t=stagger)), ("bp", 4, dict(shift_p=stagger))):
+        phi, lat, r = mesh(**sh)
+        out[name] = SphericalVariable(fields(phi, lat, r)[idx].astype(np.float32), phi, lat, r)
+    return out
