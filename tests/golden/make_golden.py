@@ -70,6 +70,19 @@ def main():
     o = sample_model_with_rays("cpu", c["x_grid"], c["y_grid"], c["z_grid"], c["ne"], c["te"], c["b"],
                                g["r_record"], g["s_record"], ray_start, r_sun_cm=6.957e10)
     np.savez_compressed(out / "sampler_on_traced_paths.npz", **o)
+    # per-frequency presets of the publication driver (script/pub/TbSpectra_gen.py:27-88).  The module
+    # imports matplotlib/astropy/psipy at top level, so only the four pure functions are extracted
+    # from its source and executed.
+    import ast
+    import json
+    src = (REF / "script" / "pub" / "TbSpectra_gen.py").read_text()
+    want = {"_lowband_params", "_interp_log_freq_params", "_highband_params", "select_params"}
+    code = "\n\n".join(ast.get_source_segment(src, n) for n in ast.parse(src).body
+                       if isinstance(n, ast.FunctionDef) and n.name in want)
+    ns = {"np": np}
+    exec(code, ns)
+    freqs = [20e6, 30e6, 75e6, 100e6, 150e6, 150.0001e6, 200e6, 279e6, 280e6, 400e6, 550e6, 700e6, 800e6, 1.2e9]
+    json.dump({repr(f): ns["select_params"](f) for f in freqs}, open(out / "select_params.json", "w"), indent=1)
     print("golden vectors written to", out)
 
 
