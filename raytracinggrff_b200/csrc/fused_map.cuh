@@ -81,7 +81,7 @@ struct RecordTransfer {
             prev = v;
             have_prev = true;
         }
-        st.apply(voxel_op(f, v));
+        st.apply(voxel_op<true>(f, v));
     }
     __device__ __forceinline__ void result(double &L, double &R) const { L = st.L[0]; R = st.R[0]; }
 };
@@ -103,7 +103,7 @@ struct OutwardTransferT : OutwardTransfer {
             prev = v;
             have_prev = true;
         }
-        fold(voxel_op(f, v));
+        fold(voxel_op<true>(f, v));
     }
     __device__ __forceinline__ void result(double &L, double &R) const { L = accL; R = accR; }
 };
@@ -161,14 +161,16 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_MINB) render_map_kernel(const Map
                 const float x = (float)s.rx, y = (float)s.ry, z = (float)s.rz, sv = (float)s_step;
                 if (sample_valid(x, y, z, sv)) {
                     ++n_samples;
-                    const FieldSample f = sample_fields(a.fcube, a.fg, x, y, z, a.fill_ne, a.fill_te, a.fill_b);
+                    float3 bv = make_float3(0.f, 0.f, 0.f);
+                    const FieldSample f = BVEC ? sample_fields_bvec(a.fcube, a.bcube, a.fg, x, y, z, a.fill_ne, a.fill_te,
+                                                                    a.fill_b, bv)
+                                               : sample_fields(a.fcube, a.fg, x, y, z, a.fill_ne, a.fill_te, a.fill_b);
                     const float dist = first ? dist_first_np(x, y, z, px, py, pz) : dist_np(x, y, z, px, py, pz);
                     const float ds = __fmul_rn(dist, a.r_sun_cm);
                     // --- Parms packing rules (script/resample_with_ray_tracing.py:472-501) ---
                     if (isfinite(f.ne) && isfinite(f.te) && isfinite(f.b)) {
                         double cth = 6.123233995736766e-17, sth = 1.0, bmag = (double)f.b;   // theta = 90 deg
                         if (BVEC) {
-                            const float3 bv = sample_bvec(a.bcube, a.fg, x, y, z);
                             const double dx = (double)x - (double)px, dy = (double)y - (double)py, dz = (double)z - (double)pz;
                             const double dn2 = dx * dx + dy * dy + dz * dz;
                             const double b2 = (double)bv.x * bv.x + (double)bv.y * bv.y + (double)bv.z * bv.z;

@@ -128,7 +128,9 @@ __device__ __forceinline__ void slab_ab(bool prop, double tau, double src, doubl
 {
     if (!prop) { a = 0.0; b = 0.0; return; }
     if (tau > 0.0) {
-        const double em = -expm1(-tau);
+        // 1 - e^-tau: four Taylor terms below 2e-3 (truncation < tau^5/120 = 3e-16), expm1 above
+        const double em = (tau < 2e-3) ? tau * (1.0 - tau * (0.5 - tau * (1.0 / 6.0 - tau * (1.0 / 24.0))))
+                                       : -expm1(-tau);
         a = 1.0 - em; b = src * em;
     } else {
         a = 1.0; b = 0.0;
@@ -152,6 +154,9 @@ __device__ __forceinline__ FreqC make_freq(double nu)
 // Uniform slab of one voxel: both magneto-ionic modes at once (same formulas as mode_eval; the
 // quantities common to the two modes — u, v, D, the Coulomb logarithm, the opacity prefactor —
 // are evaluated once).
+// FAST_T (the per-ray kernels, tolerance 1e-4 on T_b): ln T and T^-1.5 in FP32.  The kernel behind the
+// PyGET_MW / get_mw_slice ABIs keeps them FP64 (agrees with the oracle to 1e-14).
+template <bool FAST_T>
 __device__ __forceinline__ DiagOp voxel_op(const FreqC &f, const Voxel &v)
 {
     const double nuB = kNuB * v.B;
@@ -159,9 +164,19 @@ __device__ __forceinline__ DiagOp voxel_op(const FreqC &f, const Voxel &v)
     const double omv = 1.0 - vv;
     double pref = 0.0;
     if (v.ff_on) {
-        const double lnT = log(v.T);
-        const double lnL = (v.T < 2e5) ? 18.2 + 1.5 * lnT - f.ln_nu : 24.573 + lnT - f.ln_nu;
-        pref = kKff * v.ne * v.ne * kZeta * lnL * f.inv_nu2 / (v.T * sqrt(v.T));
+        if (FAST_T) {
+            // T comes from a float32 cube: its logarithm and T^-1.5 in FP32 (1e-7 relative, unbiased) save
+            // an FP64 log, sqrt and divide per voxel; everything the cut-offs depend on stays FP64
+            const float Tf = (float)v.T;
+            const double lnT = (double)logf(Tf);
+            const double lnL = (v.T < 2e5) ? 18.2 + 1.5 * lnT - f.ln_nu : 24.573 + lnT - f.ln_nu;
+            const float rs = rsqrtf(Tf);
+            pref = kKff * v.ne * v.ne * kZeta * lnL * f.inv_nu2 * (double)(rs * rs * rs);
+        } else {
+            const double lnT = log(v.T);
+            const double lnL = (v.T < 2e5) ? 18.2 + 1.5 * lnT - f.ln_nu : 24.573 + lnT - f.ln_nu;
+            pref = kKff * v.ne * v.ne * kZeta * lnL * f.inv_nu2 / (v.T * sqrt(v.T));
+        }
     }
     const double srcb = f.nu2 * kKbC2 * v.T;
     double aX = 0.0, bX = 0.0, aO = 0.0, bO = 0.0;
@@ -360,7 +375,7 @@ __global__ void __launch_bounds__(128) grff_slice_kernel(const SliceArgs a)
                     const Voxel pv = load_voxel(P + (size_t)(k - 1) * 15);
                     if (pv.ok && pv.B > 0.0 && v.B > 0.0) { bt = between_voxels(fq, pv, v); has_bt = true; }
                 }
-                op = voxel_op(fq, v);
+                op = voxel_op<false>(fq, v);
             }
         }
         const bool any_qt = __any_sync(0xffffffffu, has_bt && bt.qt);
@@ -420,7 +435,7 @@ struct OnlineTransfer {
     {
         if (!v.ok) { have_prev = false; return; }
         if (have_prev && prev.B > 0.0 && v.B > 0.0) st.apply(between_voxels(f, prev, v));
-        st.apply(voxel_op(f, v));
+        st.apply(voxel_op<true>(f, v));
         prev = v;
         have_prev = true;
     }

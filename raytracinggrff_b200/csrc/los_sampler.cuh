@@ -44,6 +44,12 @@ __device__ __forceinline__ bool cell_of(const GridGeomF &g, float px, float py, 
     return true;
 }
 
+// a*(1-t) + b*t on a channel pair, every operation rounded separately (packed FP32x2, no FMA)
+__device__ __forceinline__ float2 lerp_np2(float2 a, float2 b, float2 u, float2 t)
+{
+    return __fadd2_rn(__fmul2_rn(a, u), __fmul2_rn(b, t));
+}
+
 #define RT_TRI_NP(m)                                                                              \
     lerp_np(lerp_np(lerp_np(c000.m, c100.m, tx), lerp_np(c010.m, c110.m, tx), ty),                \
             lerp_np(lerp_np(c001.m, c101.m, tx), lerp_np(c011.m, c111.m, tx), ty), tz)
@@ -69,6 +75,56 @@ __device__ __forceinline__ FieldSample sample_fields(const float4 *__restrict__ 
     o.ne = RT_TRI_NP(x);
     o.te = RT_TRI_NP(y);
     o.b = RT_TRI_NP(z);
+    return o;
+}
+
+// n_e, T, |B| and the B vector at one point with one cell search: the two cubes share the grid.
+// Same values as sample_fields + sample_bvec (the packed operations round like the scalar ones).
+__device__ __forceinline__ FieldSample sample_fields_bvec(const float4 *__restrict__ fcube,
+                                                          const float4 *__restrict__ bcube, const GridGeomF &g,
+                                                          float px, float py, float pz, float fill_ne, float fill_te,
+                                                          float fill_b, float3 &bv)
+{
+    FieldSample o;
+    int i, j, k;
+    float tx, ty, tz;
+    o.inb = cell_of(g, px, py, pz, i, j, k, tx, ty, tz);
+    bv = make_float3(0.f, 0.f, 0.f);
+    if (!o.inb) {
+        o.ne = fill_ne; o.te = fill_te; o.b = fill_b;
+        return o;
+    }
+    const size_t sy = (size_t)g.nz, sx = (size_t)g.ny * g.nz;
+    const size_t off = (size_t)i * sx + (size_t)j * sy + (size_t)k;
+    const float2 tx2 = make_float2(tx, tx), ux2 = make_float2(__fsub_rn(1.0f, tx), __fsub_rn(1.0f, tx));
+    const float2 ty2 = make_float2(ty, ty), uy2 = make_float2(__fsub_rn(1.0f, ty), __fsub_rn(1.0f, ty));
+    const float2 tz2 = make_float2(tz, tz), uz2 = make_float2(__fsub_rn(1.0f, tz), __fsub_rn(1.0f, tz));
+#define RT_LO(c) make_float2((c).x, (c).y)
+#define RT_HI(c) make_float2((c).z, (c).w)
+#define RT_TRI_NP2(H)                                                                                         \
+    lerp_np2(lerp_np2(lerp_np2(H(c000), H(c100), ux2, tx2), lerp_np2(H(c010), H(c110), ux2, tx2), uy2, ty2),  \
+             lerp_np2(lerp_np2(H(c001), H(c101), ux2, tx2), lerp_np2(H(c011), H(c111), ux2, tx2), uy2, ty2), uz2, tz2)
+    {
+        const float4 *p = fcube + off;
+        const float4 c000 = __ldg(p), c001 = __ldg(p + 1), c010 = __ldg(p + sy), c011 = __ldg(p + sy + 1);
+        const float4 c100 = __ldg(p + sx), c101 = __ldg(p + sx + 1), c110 = __ldg(p + sx + sy),
+                     c111 = __ldg(p + sx + sy + 1);
+        const float2 nt = RT_TRI_NP2(RT_LO);
+        o.ne = nt.x; o.te = nt.y;
+        o.b = RT_TRI_NP(z);
+    }
+    {
+        const float4 *p = bcube + off;
+        const float4 c000 = __ldg(p), c001 = __ldg(p + 1), c010 = __ldg(p + sy), c011 = __ldg(p + sy + 1);
+        const float4 c100 = __ldg(p + sx), c101 = __ldg(p + sx + 1), c110 = __ldg(p + sx + sy),
+                     c111 = __ldg(p + sx + sy + 1);
+        const float2 bxy = RT_TRI_NP2(RT_LO);
+        bv.x = bxy.x; bv.y = bxy.y;
+        bv.z = RT_TRI_NP(z);
+    }
+#undef RT_TRI_NP2
+#undef RT_LO
+#undef RT_HI
     return o;
 }
 
