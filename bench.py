@@ -193,6 +193,7 @@ def config_dict(w, args):
                     f"{w['f0'] / 1e6:g}-{w['f1'] / 1e6:g} MHz, GR+FF, cross-sections on, fused trace+sample+transfer",
         "per_freq": [[p["freq_hz"], p["dt"], p["n_steps"], p["record_stride"]] for p in w["freq_params"]],
         "sharding": "rows interleaved over ranks, cube replicated, NCCL all-gather of the image",
+        "thread_order": "4x8-pixel tiles per warp (ray_order), results in row-major ray order",
         "l2": "cubes (2 x 268 MB float4 at 256^3) exceed the 126 MB L2; no flush between steps",
         "precision": "FP64 ray state and transfer, FP32 cube storage and cell-relative RHS",
         "cross_sections": "pencil rays traced on recorded steps only (the reference computes S at every step but "
@@ -282,12 +283,13 @@ def main():
             tb_ptr, vi_ptr = slab[0].data_ptr(), slab[1].data_ptr()
             _, _, st = ses.render_map(xs, ys, zs, fps, trace_crosssections=True, perturb_ratio=2.0,
                                       pixel_area_cm2=area, r_sun_cm=R_SUN_CM, em_flag=4, s_max=30, use_bvec=True,
-                                      out_device_ptrs=(tb_ptr, vi_ptr))
+                                      out_device_ptrs=(tb_ptr, vi_ptr), image_shape=(len(rows), w["n_pix_x"]))
         else:   # ragged share: render into a compact buffer, then place
             tmp = torch.empty((2, nf, len(rows), w["n_pix_x"]), dtype=torch.float64, device=dev)
             _, _, st = ses.render_map(xs, ys, zs, fps, trace_crosssections=True, perturb_ratio=2.0,
                                       pixel_area_cm2=area, r_sun_cm=R_SUN_CM, em_flag=4, s_max=30, use_bvec=True,
-                                      out_device_ptrs=(tmp[0].data_ptr(), tmp[1].data_ptr()))
+                                      out_device_ptrs=(tmp[0].data_ptr(), tmp[1].data_ptr()),
+                                      image_shape=(len(rows), w["n_pix_x"]))
             slab[:, :, :len(rows)] = tmp
         stats_box.update(st)
         stats_box["kernel_ms"] = ses.ctx.last_kernel_ms

@@ -183,13 +183,16 @@ typedef struct {
  * run_ray_tracing_emission (script/resample_with_ray_tracing.py:295-530) called once per frequency
  * as the publication drivers do (script/pub/TbSpectra_gen.py:155-182).
  *  Rays: x_start,y_start,z_start host float64 (n_rays), direction (0,0,-1) unless kvec != NULL.
+ *  ray_order (host int32 (n_rays), a permutation, or NULL): thread t works on ray ray_order[t]; inputs
+ *  and outputs keep the caller's ray numbering.  Walking an image in small 2-D tiles instead of rows
+ *  puts 32 neighbouring pixels into a warp and cuts the distinct cube cells it gathers from.
  *  use_bvec: 0 -> theta=90 deg (reference behaviour); 1 -> theta from B.t along the ray (needs bx,by,bz).
  *  tb, vi: float64 (n_freq, n_rays); host, or device pointers when out_on_device != 0.
  *  stats (optional, host int64[4]): {nominal ray-steps, active ray-steps (the ray still moved),
  *  steps on which the two cross-section rays were traced, valid samples handed to the transfer}.
  */
 int rtgrff_render_map(rtgrff_ctx *ctx, int64_t n_rays, const double *x_start, const double *y_start,
-                      const double *z_start, const double *kvec, int n_freq,
+                      const double *z_start, const double *kvec, const int32_t *ray_order, int n_freq,
                       const rtgrff_freq_params *freqs, int trace_cs, double perturb_ratio,
                       double pixel_area_cm2, double r_sun_cm, int em_flag, int s_max, int use_bvec,
                       int voxel_order, double *tb, double *vi, int out_on_device, int64_t *stats);

@@ -83,7 +83,7 @@ def load():
     lib.PyGET_MW.restype = c_int
     lib.rtgrff_get_mw_slice.argtypes = [c_void_p, ip, dp, dp, dp, dp, dp, dp, ip]
     lib.rtgrff_emission_traced.argtypes = [c_void_p, c_double, c_double, c_int, c_double, c_int, c_int, dp, dp]
-    lib.rtgrff_render_map.argtypes = [c_void_p, c_int64, dp, dp, dp, dp, c_int, POINTER(FreqParams), c_int, c_double,
+    lib.rtgrff_render_map.argtypes = [c_void_p, c_int64, dp, dp, dp, dp, ip, c_int, POINTER(FreqParams), c_int, c_double,
                                       c_double, c_double, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
                                       POINTER(c_int64)]
     for name in EXPORTS:

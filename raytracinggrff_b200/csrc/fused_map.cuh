@@ -30,6 +30,7 @@ struct MapArgs {
     GridGeomF fg;
     int64_t n_rays;
     const double *x_start, *y_start, *z_start, *kvec;
+    const int *ray_order;                // thread t handles ray ray_order[t] (nullptr: t); see rtgrff.h
     int n_freq;
     const FreqDev *freqs;
     double perturb_ratio, area;
@@ -112,9 +113,10 @@ template <bool CS, int ORDER, bool BVEC, bool GR, int MODE>
 __global__ void __launch_bounds__(RT_BLOCK, RT_MINB) render_map_kernel(const MapArgs a)
 {
     constexpr bool NEED_BETWEEN = BVEC || GR;
-    const int64_t ray = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int fi = blockIdx.y;
-    const bool has_ray = ray < a.n_rays;
+    const bool has_ray = slot < a.n_rays;
+    const int64_t ray = (has_ray && a.ray_order) ? (int64_t)a.ray_order[slot] : slot;
     const RayCube &C = a.cube;
     const FreqDev fp = a.freqs[fi];
     const StepConst K = make_step_const(C, fp.dt, a.perturb_ratio);

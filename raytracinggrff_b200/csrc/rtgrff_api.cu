@@ -584,7 +584,8 @@ int rtgrff_emission_traced(rtgrff_ctx *c, double pixel_area_cm2, double freq0_hz
 }
 
 int rtgrff_render_map(rtgrff_ctx *c, int64_t n_rays, const double *x_start, const double *y_start,
-                      const double *z_start, const double *kvec, int n_freq, const rtgrff_freq_params *freqs,
+                      const double *z_start, const double *kvec, const int32_t *ray_order, int n_freq,
+                      const rtgrff_freq_params *freqs,
                       int trace_cs, double perturb_ratio, double pixel_area_cm2, double r_sun_cm, int em_flag, int s_max,
                       int use_bvec, int voxel_order, double *tb, double *vi, int out_on_device, int64_t *stats)
 {
@@ -614,6 +615,10 @@ int rtgrff_render_map(rtgrff_ctx *c, int64_t n_rays, const double *x_start, cons
     RT_TRY(h2d(c, c->in1, y_start, nb));
     RT_TRY(h2d(c, c->in2, z_start, nb));
     if (kvec) RT_TRY(h2d(c, c->in3, kvec, 3 * nb));
+    if (ray_order) {
+        if (n_rays >= ((int64_t)1 << 31)) return fail(RTGRFF_EINVAL, "ray_order needs n_rays < 2^31");
+        RT_TRY(h2d(c, c->out2, ray_order, (size_t)n_rays * sizeof(int32_t)));
+    }
     RT_TRY(c->counters.reserve(64 + (size_t)n_freq * sizeof(FreqDev)));
     RT_CUDA(cudaMemsetAsync(c->counters.p, 0, 64, c->stream));
     FreqDev *dfreq = reinterpret_cast<FreqDev *>(c->counters.as<char>() + 64);
@@ -632,6 +637,7 @@ int rtgrff_render_map(rtgrff_ctx *c, int64_t n_rays, const double *x_start, cons
     a.n_rays = n_rays;
     a.x_start = c->in0.as<double>(); a.y_start = c->in1.as<double>(); a.z_start = c->in2.as<double>();
     a.kvec = kvec ? c->in3.as<double>() : nullptr;
+    a.ray_order = ray_order ? c->out2.as<int>() : nullptr;
     a.n_freq = n_freq; a.freqs = dfreq;
     a.perturb_ratio = perturb_ratio; a.area = pixel_area_cm2;
     a.r_sun_cm = (float)r_sun_cm; a.fill_ne = 0.0f; a.fill_te = 1e4f; a.fill_b = 0.0f;

@@ -167,11 +167,14 @@ class RaySession:
     # -- fused map -----------------------------------------------------------------------------
     def render_map(self, x_start, y_start, z_start, freq_params, kvec_in_norm=None, trace_crosssections=True,
                    perturb_ratio=2.0, pixel_area_cm2=1.0, r_sun_cm=6.957e10, em_flag=5, s_max=30, use_bvec=False,
-                   voxel_order=_lib.ORDER_RECORD, out_device_ptrs=None):
+                   voxel_order=_lib.ORDER_RECORD, out_device_ptrs=None, image_shape=None, tile=(4, 8), ray_order=None):
         """Fused trace+sample+transfer.  freq_params: sequence of dicts/tuples
         (freq_hz, dt, n_steps, record_stride).  Returns (tb, vi) each (n_freq, n_rays) float64 and
         stats {nominal_ray_steps, active_ray_steps}; with out_device_ptrs=(tb_ptr, vi_ptr) the
-        results are written to those device buffers instead and (None, None, stats) is returned."""
+        results are written to those device buffers instead and (None, None, stats) is returned.
+        image_shape=(n_rows, n_cols): the rays are a row-major image (ray p = i*n_cols + j); threads
+        then walk it in `tile` = (width, height) pixel tiles, which keeps a warp's 32 rays in a compact
+        patch (-11 % on config 4); results keep the caller's ray numbering."""
         xs, ys, zs = f64(x_start).ravel(), f64(y_start).ravel(), f64(z_start).ravel()
         n_rays = xs.shape[0]
         kv = None
@@ -179,6 +182,17 @@ class RaySession:
             kv = f64(kvec_in_norm)
             if kv.shape != (n_rays, 3):
                 raise ValueError(f"kvec_in_norm must have shape ({n_rays}, 3)")
+        order = None
+        if ray_order is not None:
+            order = np.ascontiguousarray(ray_order, dtype=np.int32)
+        elif image_shape is not None and tile is not None:
+            n_rows, n_cols = image_shape
+            if n_rows * n_cols != n_rays:
+                raise ValueError("image_shape does not match the number of rays")
+            from .synthetic import tile_order
+            order = tile_order(n_cols, n_rows, tile[0], tile[1]).astype(np.int32)
+        if order is not None and order.shape != (n_rays,):
+            raise ValueError("ray_order must be a permutation of the rays")
         nf = len(freq_params)
         arr = (FreqParams * nf)()
         for i, p in enumerate(freq_params):
@@ -194,7 +208,7 @@ class RaySession:
             tb = vi = None
             ptb, pvi, on_dev = ctypes.c_void_p(out_device_ptrs[0]), ctypes.c_void_p(out_device_ptrs[1]), 1
         check(self._lib.rtgrff_render_map(self.ctx.handle, n_rays, ptr(xs, c_double), ptr(ys, c_double),
-                                          ptr(zs, c_double), ptr(kv, c_double), nf, arr,
+                                          ptr(zs, c_double), ptr(kv, c_double), ptr(order, ctypes.c_int32), nf, arr,
                                           int(bool(trace_crosssections)), float(perturb_ratio), float(pixel_area_cm2),
                                           float(r_sun_cm), int(em_flag), int(s_max), int(bool(use_bvec)),
                                           int(voxel_order), ptb, pvi, on_dev, stats))

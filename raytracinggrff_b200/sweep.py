@@ -103,7 +103,7 @@ def tb_spectra(model, out_dir, N_pix=128, fmin_mhz=30.0, fmax_mhz=800.0, n_freq=
             tb, vi, _ = ses.render_map(xs, ys, zs, [(float(freq_hz), float(p["dt"]), int(p["n_steps"]),
                                                      int(p["record_stride"]))], kvec_in_norm=kv,
                                        trace_crosssections=True, perturb_ratio=2.0, pixel_area_cm2=area,
-                                       r_sun_cm=R_sun_cm, em_flag=em_flag, use_bvec=use_bvec)
+                                       r_sun_cm=R_sun_cm, em_flag=em_flag, use_bvec=use_bvec, image_shape=(N_pix, N_pix))
             coords = np.linspace(-p["x_fov"], p["x_fov"], N_pix) * R_sun_m
             np.savez_compressed(npz_path,                                    # script/...:533-540
                                 emission_cube=np.nan_to_num(tb[0].reshape(N_pix, N_pix, 1), nan=0.0, posinf=0.0, neginf=0.0),

@@ -17,6 +17,8 @@ active-region dipole so that gyroresonance matters at GHz frequencies).
 """
 from __future__ import annotations
 
+import functools
+
 import numpy as np
 
 R_MIN = 0.999999          # script/resample_with_ray_tracing.py:71
@@ -158,6 +160,7 @@ def los_sampler_case(n_pix=256, n_steps=256, grid_n=128, seed=0):
     return g, g.copy(), g.copy(), ne, te, b, r_record, s_arr, origin
 
 
+@functools.lru_cache(maxsize=16)
 def tile_order(n_x, n_y, tile_w=8, tile_h=4):
     """Permutation of the flat pixel indices p = i*n_x + j that walks the image in tile_w x tile_h
     pixel tiles (row-major inside a tile): with one thread per ray, a warp of 32 consecutive rays

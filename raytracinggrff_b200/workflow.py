@@ -118,7 +118,7 @@ def run_ray_tracing_emission(model, N_pix=64, X_fov=1.44, freq_hz=75e6, z_observ
                              "(or RaySession.render_map for a list of frequencies)")
         tb, vi, _ = ses.render_map(x_flat, y_flat, z_start, [(freq_hz, dt, n_steps, record_stride)],
                                    kvec_in_norm=kvec, trace_crosssections=True, perturb_ratio=perturb_ratio,
-                                   pixel_area_cm2=area, r_sun_cm=R_sun_cm)
+                                   pixel_area_cm2=area, r_sun_cm=R_sun_cm, image_shape=(N_pix, N_pix))
         emission_cube[:, :, 0] = tb[0].reshape(N_pix, N_pix)
         emission_polVI_cube[:, :, 0] = vi[0].reshape(N_pix, N_pix)
     else:

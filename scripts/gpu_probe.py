@@ -66,6 +66,12 @@ def main():
         ses.set_omega_cube(c["omega_pe"], c["x_grid"], c["y_grid"], c["z_grid"])
         ses.set_field_cubes(c["x_grid"], c["y_grid"], c["z_grid"], c["ne"], c["te"], c["b"], c["bx"], c["by"], c["bz"])
         xs, ys, zs, kv = synthetic.ray_launch_geometry(512, 1.44, 3.0)
+        tile = os.environ.get("RTGRFF_TILE")
+        if tile:
+            tw, th = (int(t) for t in tile.split("x"))
+            perm = synthetic.tile_order(512, 512, tw, th)
+            xs, ys, zs = xs[perm], ys[perm], zs[perm]
+            print("tile order", tile)
         area = (2 * 1.44 / 512 * 6.957e10) ** 2
         freqs = synthetic.log_frequencies(75e6, 8, np.log10(20.0) / 7)
         for label, kw in (("GR+FF bvec", dict(em_flag=4, use_bvec=True)), ("FF theta90", dict(em_flag=5, use_bvec=False))):
