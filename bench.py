@@ -194,7 +194,9 @@ def config_dict(w, args):
         "per_freq": [[p["freq_hz"], p["dt"], p["n_steps"], p["record_stride"]] for p in w["freq_params"]],
         "sharding": "rows interleaved over ranks, cube replicated, NCCL all-gather of the image",
         "thread_order": "4x8-pixel tiles per warp (ray_order), results in row-major ray order",
-        "l2": "cubes (2 x 268 MB float4 at 256^3) exceed the 126 MB L2; no flush between steps",
+        "l2": f"cubes (3 x {16 * w['grid_n'] ** 3 / 1e6:.0f} MB float4) exceed the 126 MB L2; no flush between steps",
+        "cubes": "built on the GPU from a spherical (phi,lat,r) model" if (w["name"] == "config5" or args.spherical)
+                 else "analytic corona, uploaded from pinned host memory",
         "precision": "FP64 ray state and transfer, FP32 cube storage and cell-relative RHS",
         "cross_sections": "pencil rays traced on recorded steps only (the reference computes S at every step but "
                           "outputs only recorded steps, build_rays.py:241-244); RTGRFF_CS_EVERY_STEP=1 restores it",
@@ -211,6 +213,7 @@ def main():
     ap.add_argument("--cpu-sample-stride", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--spherical", action="store_true", help="build the cubes on the GPU from a spherical model")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     w = workload(args.config, args.gpus)
@@ -246,7 +249,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    cube = synthetic.corona_cube(w["grid_n"], w["extent"], active_region=True)
+    # config 5 (512^3): the cubes are built on the GPU from a spherical (phi, lat, r) model — the
+    # reference's own pipeline shape (MAS model -> resample -> trace) — instead of 6 x 1 GB host cubes
+    spherical = w["name"] == "config5" or args.spherical
+    cube = None if spherical else synthetic.corona_cube(w["grid_n"], w["extent"], active_region=True)
     stream = torch.cuda.current_stream().cuda_stream
     ses = RaySession(context=_lib.Context(local_rank, stream))
     idx, rows = rdist.shard_rays(w["n_pix_x"], w["n_pix_y"], world, rank)
@@ -265,13 +271,23 @@ def main():
         t.copy_(torch.from_numpy(np.ascontiguousarray(a)))
         return t.numpy()
 
-    h_w = pinned(cube["omega_pe"], torch.float64)
-    h_f = {k: pinned(cube[k], torch.float32) for k in ("ne", "te", "b", "bx", "by", "bz")}
-    grids = (cube["x_grid"], cube["y_grid"], cube["z_grid"])
+    if spherical:
+        model = synthetic.spherical_corona(200, 140, 160, r_max=1.8 * w["extent"], active_region=True)
+        gline = np.linspace(-w["extent"], w["extent"], w["grid_n"])
+        grids = (gline, gline.copy(), gline.copy())
+        h2d_cubes = sum(v.data.nbytes + v.phi.nbytes + v.lat.nbytes + v.r.nbytes for v in model.values())
 
-    def upload():
-        ses.set_omega_cube(h_w, *grids)
-        ses.set_field_cubes(*grids, h_f["ne"], h_f["te"], h_f["b"], h_f["bx"], h_f["by"], h_f["bz"])
+        def upload():
+            ses.set_model_from_spherical(model, *grids, phi0_offset=0.0, want_bvec=True)
+    else:
+        h_w = pinned(cube["omega_pe"], torch.float64)
+        h_f = {k: pinned(cube[k], torch.float32) for k in ("ne", "te", "b", "bx", "by", "bz")}
+        grids = (cube["x_grid"], cube["y_grid"], cube["z_grid"])
+        h2d_cubes = h_w.nbytes + sum(a.nbytes for a in h_f.values())
+
+        def upload():
+            ses.set_omega_cube(h_w, *grids)
+            ses.set_field_cubes(*grids, h_f["ne"], h_f["te"], h_f["b"], h_f["bx"], h_f["by"], h_f["bz"])
 
     # device-side image slabs: [2 (tb, vi)][freq][rows_max][n_pix_x]
     slab = torch.zeros((2, nf, mr, w["n_pix_x"]), dtype=torch.float64, device=dev)
@@ -336,7 +352,7 @@ def main():
     value = nominal_total / (ms_per_step * 1e-3)
 
     # ---- end to end: host cubes in, host maps out, every step ----
-    h2d = h_w.nbytes + sum(a.nbytes for a in h_f.values()) + 3 * 8 * n_local
+    h2d = h2d_cubes + 3 * 8 * n_local
     d2h = 2 * nf * w["n_pix_x"] * w["n_pix_y"] * 8 if rank == 0 else 0
     for _ in range(1):
         upload(); render()
@@ -366,9 +382,11 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
-        traffic = None
+        traffic = None      # dram__bytes of one launch from the committed ncu capture of exactly this workload
         try:
-            traffic = json.load(open(ROOT / "profiles" / "roofline_traffic.json")).get("render_map_kernel_dram_bytes_per_launch")
+            tj = json.load(open(ROOT / "profiles" / "roofline_traffic.json"))
+            if tj.get("workload") == f"{w['name']}/{world}gpu":
+                traffic = tj.get("render_map_kernel_dram_bytes_per_launch")
         except Exception:
             pass
         # algorithmic bytes per launch (one launch per rank per step), SURVEY 8d per-unit figures x the units
@@ -400,7 +418,7 @@ def main():
         if not args.no_cpu_baseline:
             from oracle import oracle
             oracle.build()
-            cpu_reference_step.cube = cube
+            cpu_reference_step.cube = cube if cube is not None else synthetic.corona_cube(w["grid_n"], w["extent"], active_region=True)
             n, tcpu, n_rays = cpu_reference_step(workload(args.config, 1), args.cpu_sample_stride)
             line["cpu_baseline"] = {
                 "value": n / tcpu, "unit": "ray-steps/s", "cores": os.cpu_count(), "kind": "port",
