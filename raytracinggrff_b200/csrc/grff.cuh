@@ -185,31 +185,34 @@ __device__ __forceinline__ DiagOp voxel_op(const FreqC &f, const Voxel &v)
         const double us2 = u * s2;
         const double sD = sqrt(us2 * us2 + 4.0 * u * omv * omv * c2);
         const double num0 = us2 + 2.0 * omv * omv, base = 2.0 * omv - us2;
+        const double inv_sD = 1.0 / sD, us4 = us2 * us2, vo2 = 2.0 * vv * omv;
+        // n^2 = 1 - 2 v (1-v)/den,  F = 2 (num0 -+ us2^2/sD) / den^2  with den = base -+ sD: one reciprocal
+        // per mode and one shared 1/sD instead of four divisions, rsqrt instead of sqrt + divide
         // X mode (sigma = -1): cut off for nu <= nu_B or v >= 1 - sqrt(u)
         if (!(u >= 1.0 || vv >= 1.0 - sqrt(u))) {
-            const double den = base - sD;
-            const double n2 = 1.0 - 2.0 * vv * omv / den;
-            const double F = 2.0 * (-sD * num0 - us2 * us2) / (-sD * den * den);
+            const double inv_den = 1.0 / (base - sD);
+            const double n2 = 1.0 - vo2 * inv_den;
+            const double F = 2.0 * (num0 + us4 * inv_sD) * inv_den * inv_den;
             if (n2 > 0.0 && isfinite(n2) && isfinite(F)) {
-                double kap = pref * F / sqrt(n2);
+                double kap = pref * F * rsqrt(n2);
                 if (!(kap > 0.0) || !isfinite(kap)) kap = 0.0;
                 slab_ab(true, kap * v.dz, n2 * srcb, aX, bX);
             }
         }
         // O mode (sigma = +1): cut off for v >= 1
         if (vv < 1.0) {
-            const double den = base + sD;
-            const double n2 = 1.0 - 2.0 * vv * omv / den;
-            const double F = 2.0 * (sD * num0 - us2 * us2) / (sD * den * den);
+            const double inv_den = 1.0 / (base + sD);
+            const double n2 = 1.0 - vo2 * inv_den;
+            const double F = 2.0 * (num0 - us4 * inv_sD) * inv_den * inv_den;
             if (n2 > 0.0 && isfinite(n2) && isfinite(F)) {
-                double kap = pref * F / sqrt(n2);
+                double kap = pref * F * rsqrt(n2);
                 if (!(kap > 0.0) || !isfinite(kap)) kap = 0.0;
                 slab_ab(true, kap * v.dz, n2 * srcb, aO, bO);
             }
         }
     } else if (vv < 1.0) {
         // B = 0: one refractive index, unpolarised
-        double kap = pref / sqrt(omv);
+        double kap = pref * rsqrt(omv);
         if (!(kap > 0.0) || !isfinite(kap)) kap = 0.0;
         slab_ab(true, kap * v.dz, omv * srcb, aX, bX);
         aO = aX; bO = bX;
