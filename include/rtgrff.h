@@ -92,6 +92,18 @@ int rtgrff_resample_spherical(rtgrff_ctx *ctx, int slot, const float *data, cons
                               double scale, double fill, int fill_nonfinite, double *out);
 
 /*
+ * Sample one spherical variable along straight lines of sight (the resampler of the straight-LOS
+ * workflow, script/resampling_MAS_LOS.py:141-231): pixel (i,j) at (x[j], y[i]) [R_sun]; each LOS
+ * starts on the solar surface / the plane of the sky behind the limb, minus z_eps, and runs towards
+ * the observer over the offsets zc[k] [R_sun]; r < r_min or outside the mesh -> NaN.
+ *  out: host float64 (ny, nx, nz).
+ */
+int rtgrff_sample_spherical_los(rtgrff_ctx *ctx, const float *data, const double *phi, const double *lat,
+                                const double *r, int np, int nt, int nr, const double *x, const double *y,
+                                const double *zc, int nx, int ny, int nz, double phi0_offset_deg,
+                                double r_min, double scale, double z_eps, double *out);
+
+/*
  * Build the device cubes of the ray path from the five resampled slots with the reference's rules
  * (script/resample_with_ray_tracing.py:269-293): omega_pe = 2 pi 8.93e3 sqrt(max(rho,0)) (NaN -> 0)
  * and its numpy.gradient, n_e = max(rho,0), T NaN -> 1e4, |B| = sqrt(br^2+bt^2+bp^2); with

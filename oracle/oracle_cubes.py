@@ -66,3 +66,41 @@ def compose_cubes(model, x_grid, y_grid, z_grid, phi0_offset=0.0, r_min=0.999999
     br, bt, bp = (resample_to_xyz_cube(model[k], x_grid, y_grid, z_grid, phi0_offset, 0.0, r_min) for k in ("br", "bt", "bp"))
     b = np.sqrt(br ** 2 + bt ** 2 + bp ** 2)
     return dict(x_grid=x_grid, y_grid=y_grid, z_grid=z_grid, omega_pe=omega_pe, ne=ne, te=te, b=b, br=br, bt=bt, bp=bp)
+
+
+def resample_MAS(model, N_pix, X_range, Y_range, N_z, dz0, phi0_offset=0.0, r_min=0.9999999):
+    """script/resampling_MAS_LOS.py:141-301 restated (variable z spacing): per-pixel straight LOS
+    sampling of rho, te, br, bt, bp; returns the LOS_data dict."""
+    R_sun_m, R_sun_cm = 6.957e8, 6.957e10
+    idx_z = np.arange(N_z)
+    dz = dz0 * (1 + (5 * idx_z / N_z) ** 2.5)
+    z_coords = np.cumsum(dz) * R_sun_m
+    x_coords = np.linspace(X_range[0], X_range[1], N_pix) * R_sun_m
+    y_coords = np.linspace(Y_range[0], Y_range[1], N_pix) * R_sun_m
+    X, Y = np.meshgrid(x_coords, y_coords)
+    temp = "te" if "te" in model else "t"
+    shape = (N_pix, N_pix, N_z)
+    Ne, Te, B = (np.full(shape, np.nan) for _ in range(3))
+    ds = np.zeros(shape)
+    for k in range(N_z):
+        ds[:, :, k] = dz[k] * R_sun_cm
+    for i in range(N_pix):
+        for j in range(N_pix):
+            x, y = X[i, j], Y[i, j]
+            if np.sqrt(x ** 2 + y ** 2) < R_sun_m:
+                z_start = np.sqrt(R_sun_m ** 2 - (x ** 2 + y ** 2)) - 1e-6
+            else:
+                z_start = -np.sqrt(x ** 2 + y ** 2 - R_sun_m ** 2) - 1e-6
+            z_arr = z_start + z_coords
+            r_m, colat, lon = cart_to_sph(np.full(N_z, x), -z_arr, np.full(N_z, y), phi0_offset)
+            r = r_m / R_sun_m
+            valid = r >= r_min
+            if not np.any(valid):
+                continue
+            lat = np.pi / 2 - colat
+            Ne[i, j] = sample_at_coords(model["rho"], lon, lat, r)
+            Te[i, j] = sample_at_coords(model[temp], lon, lat, r)
+            B[i, j] = np.sqrt(sum(sample_at_coords(model[c], lon, lat, r) ** 2 for c in ("br", "bt", "bp")))
+            for a in (Ne, Te, B):
+                a[i, j, ~valid] = np.nan
+    return dict(Ne_LOS=Ne, Te_LOS=Te, B_LOS=B, ds_LOS=ds, x_coords=x_coords, y_coords=y_coords, z_coords=z_coords)

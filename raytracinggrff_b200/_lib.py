@@ -33,7 +33,7 @@ ORDER_REVERSED = 1
 EXPORTS = (
     "rtgrff_version", "rtgrff_last_error", "rtgrff_device_count", "rtgrff_ctx_create", "rtgrff_ctx_destroy",
     "rtgrff_ctx_synchronize", "rtgrff_ctx_launch_count", "rtgrff_ctx_last_kernel_ms", "rtgrff_set_omega_cube", "rtgrff_set_field_cubes",
-    "rtgrff_resample_spherical", "rtgrff_compose_cubes",
+    "rtgrff_resample_spherical", "rtgrff_compose_cubes", "rtgrff_sample_spherical_los",
     "rtgrff_trace", "rtgrff_sample", "rtgrff_sample_traced", "PyGET_MW", "rtgrff_get_mw_slice",
     "rtgrff_emission_traced", "rtgrff_render_map",
 )
@@ -73,6 +73,8 @@ def load():
     lib.rtgrff_resample_spherical.argtypes = [c_void_p, c_int, fp, dp, dp, dp, c_int, c_int, c_int, dp, dp, dp, c_int,
                                               c_int, c_int, dp, c_double, c_double, c_double, c_double, c_int, dp]
     lib.rtgrff_compose_cubes.argtypes = [c_void_p, c_int]
+    lib.rtgrff_sample_spherical_los.argtypes = [c_void_p, fp, dp, dp, dp, c_int, c_int, c_int, dp, dp, dp, c_int, c_int,
+                                                c_int, c_double, c_double, c_double, c_double, dp]
     lib.rtgrff_trace.argtypes = [c_void_p, c_int64, dp, dp, dp, dp, c_double, c_double, c_int64, c_int64, c_int,
                                  c_double, c_int, dp, dp, POINTER(c_int64)]
     lib.rtgrff_sample.argtypes = [c_void_p, c_int64, c_int64, fp, fp, fp, c_double, c_double, c_double, c_double,

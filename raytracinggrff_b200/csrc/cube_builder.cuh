@@ -106,6 +106,40 @@ __global__ void __launch_bounds__(256) resample_spherical_kernel(const ResampleA
     }
 }
 
+// Straight line-of-sight sampling of one spherical variable (script/resampling_MAS_LOS.py:141-231):
+// pixel (i,j) at (x[j], y[i]); the LOS starts on the solar surface (inside the disk) or on the plane
+// of the sky behind the limb (:198-201) and runs towards the observer over the z offsets zc[k];
+// position -> cart_to_sph(x, -z, y, phi0) (:208); r < r_min -> NaN (:210-218).
+struct LosArgs {
+    SphMesh mesh;
+    const double *x, *y, *zc;     // R_sun: pixel columns, pixel rows, cumulative z offsets
+    int nx, ny, nz;
+    double phi0_offset_rad, r_min, scale, z_eps;   // z_eps = 1e-6 m in R_sun (:199, :201)
+    double *out;                  // [ny][nx][nz]
+};
+
+__global__ void __launch_bounds__(256) los_spherical_kernel(const LosArgs a)
+{
+    const int64_t total = (int64_t)a.ny * a.nx * a.nz;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total;
+         q += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(q % a.nz), j = (int)((q / a.nz) % a.nx), i = (int)(q / ((int64_t)a.nx * a.nz));
+        const double x = a.x[j], y = a.y[i];
+        const double rho2 = x * x + y * y;
+        const double z0 = (sqrt(rho2) < 1.0) ? sqrt(1.0 - rho2) - a.z_eps : -sqrt(rho2 - 1.0) - a.z_eps;
+        const double z = z0 + a.zc[k];
+        const double cx = x, cy = -z, cz = y;
+        const double r = sqrt(cx * cx + cy * cy + cz * cz);
+        const double colat = acos(fmin(1.0, fmax(-1.0, cz / r)));
+        double lon = atan2(cy, cx) + a.phi0_offset_rad;
+        if (lon < 0.0) lon += 6.283185307179586476925286766559;
+        const double lat = 1.5707963267948966192313216916398 - colat;
+        double v = nan("");
+        if (r >= a.r_min) v = sample_spherical(a.mesh, lon, lat, r) * a.scale;
+        a.out[q] = v;
+    }
+}
+
 // script/resample_with_ray_tracing.py:269-293 on device: rho -> omega_pe (f64, for the gradient
 // kernel) and n_e >= 0; T NaN -> 1e4; |B| = sqrt(br^2+bt^2+bp^2); optional Cartesian B vector.
 struct ComposeArgs {

@@ -323,6 +323,53 @@ int rtgrff_resample_spherical(rtgrff_ctx *c, int slot, const float *data, const 
     return RTGRFF_OK;
 }
 
+int rtgrff_sample_spherical_los(rtgrff_ctx *c, const float *data, const double *phi, const double *lat, const double *r,
+                                int np, int nt, int nr, const double *x, const double *y, const double *zc, int nx,
+                                int ny, int nz, double phi0_offset_deg, double r_min, double scale, double z_eps,
+                                double *out)
+{
+    RT_TRY(use(c));
+    if (!data || !phi || !lat || !r || !x || !y || !zc || !out) return fail(RTGRFF_EINVAL, "null argument");
+    if (np < 2 || nt < 2 || nr < 2 || nx < 1 || ny < 1 || nz < 1) return fail(RTGRFF_EINVAL, "bad sizes");
+    for (int i = 1; i < np; ++i) if (!(phi[i] > phi[i - 1])) return fail(RTGRFF_EINVAL, "phi nodes must ascend");
+    for (int i = 1; i < nt; ++i) if (!(lat[i] > lat[i - 1])) return fail(RTGRFF_EINVAL, "latitude nodes must ascend");
+    for (int i = 1; i < nr; ++i) if (!(r[i] > r[i - 1])) return fail(RTGRFF_EINVAL, "radius nodes must ascend");
+    const size_t total = (size_t)nx * ny * nz, nd = (size_t)np * nt * nr;
+    RT_TRY(h2d(c, c->in0, data, nd * sizeof(float)));
+    RT_TRY(c->in1.reserve((size_t)(np + nt + nr + nx + ny + nz) * sizeof(double)));
+    double *ax = c->in1.as<double>();
+    const double *src[6] = {phi, lat, r, x, y, zc};
+    const int len[6] = {np, nt, nr, nx, ny, nz};
+    double *dst[6];
+    size_t o = 0;
+    for (int q = 0; q < 6; ++q) {
+        dst[q] = ax + o;
+        RT_CUDA(cudaMemcpyAsync(dst[q], src[q], len[q] * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        o += len[q];
+    }
+    RT_TRY(c->out0.reserve(total * sizeof(double)));
+    LosArgs a;
+    a.mesh.data = c->in0.as<float>();
+    a.mesh.phi = dst[0]; a.mesh.lat = dst[1]; a.mesh.r = dst[2];
+    a.mesh.np = np; a.mesh.nt = nt; a.mesh.nr = nr;
+    a.x = dst[3]; a.y = dst[4]; a.zc = dst[5];
+    a.nx = nx; a.ny = ny; a.nz = nz;
+    a.phi0_offset_rad = phi0_offset_deg * M_PI / 180.0;
+    a.r_min = r_min; a.scale = scale; a.z_eps = z_eps;
+    a.out = c->out0.as<double>();
+    unsigned int blocks = blocks_for((int64_t)total, 256);
+    const unsigned int cap = (unsigned int)c->sm_count * 32;
+    if (blocks > cap) blocks = cap;
+    RT_CUDA(cudaEventRecord(c->ev0, c->stream));
+    los_spherical_kernel<<<blocks, 256, 0, c->stream>>>(a);
+    RT_TRY(launched(c, "los_spherical_kernel"));
+    RT_CUDA(cudaEventRecord(c->ev1, c->stream));
+    c->ev_valid = true;
+    RT_TRY(d2h(c, out, c->out0.p, total * sizeof(double)));
+    RT_CUDA(cudaStreamSynchronize(c->stream));
+    return RTGRFF_OK;
+}
+
 int rtgrff_compose_cubes(rtgrff_ctx *c, int want_bvec)
 {
     RT_TRY(use(c));
