@@ -19,10 +19,17 @@
 
 namespace rtgrff {
 
+// Everything that depends on the frequency only, prepared on the host and passed BY VALUE inside
+// the kernel parameters (constant bank, indexed by blockIdx.y): the ~20 registers these constants
+// used to occupy per thread were spilled around the record-time code.
 struct FreqDev {
     double nu, omega0, dt;
     int64_t n_steps, stride;
+    StepConst K;
+    FreqC fq;
 };
+
+constexpr int kMaxFreqPerLaunch = 16;
 
 struct MapArgs {
     RayCube cube;
@@ -31,8 +38,9 @@ struct MapArgs {
     int64_t n_rays;
     const double *x_start, *y_start, *z_start, *kvec;
     const int *ray_order;                // thread t handles ray ray_order[t] (nullptr: t); see rtgrff.h
-    int n_freq;
-    const FreqDev *freqs;
+    int n_freq;                          // <= kMaxFreqPerLaunch
+    int freq_base;                       // index of freqs[0] in the caller's frequency list (output row)
+    FreqDev freqs[kMaxFreqPerLaunch];
     double perturb_ratio, area;
     float r_sun_cm, fill_ne, fill_te, fill_b;
     int em_flag, s_max, use_bvec, order, cs_every_step;
@@ -118,9 +126,9 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_MINB) render_map_kernel(const Map
     const bool has_ray = slot < a.n_rays;
     const int64_t ray = (has_ray && a.ray_order) ? (int64_t)a.ray_order[slot] : slot;
     const RayCube &C = a.cube;
-    const FreqDev fp = a.freqs[fi];
-    const StepConst K = make_step_const(C, fp.dt, a.perturb_ratio);
-    const FreqC fq = make_freq(fp.nu);
+    const FreqDev &fp = a.freqs[fi];
+    const StepConst &K = fp.K;
+    const FreqC &fq = fp.fq;
     Cell cache;
     cache.off = -1;
 
@@ -199,8 +207,8 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_MINB) render_map_kernel(const Map
         double tb, vi, IL, IR;
         tr.result(IL, IR);
         tb_vi(IL, IR, fp.nu, a.area, tb, vi);
-        a.tb[(size_t)fi * a.n_rays + ray] = tb;
-        a.vi[(size_t)fi * a.n_rays + ray] = vi;
+        a.tb[(size_t)(a.freq_base + fi) * a.n_rays + ray] = tb;
+        a.vi[(size_t)(a.freq_base + fi) * a.n_rays + ray] = vi;
     }
     if (a.active_steps) {
         unsigned long long ps = pencil_steps, ns = n_samples;

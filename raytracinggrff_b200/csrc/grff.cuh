@@ -143,7 +143,7 @@ struct FreqC {
     double sn;    // kBres * nu: resonant field of harmonic s is sn / s
 };
 
-__device__ __forceinline__ FreqC make_freq(double nu)
+__host__ __device__ __forceinline__ FreqC make_freq(double nu)
 {
     FreqC f;
     f.nu = nu; f.nu2 = nu * nu; f.inv_nu2 = 1.0 / f.nu2; f.ln_nu = log(nu);

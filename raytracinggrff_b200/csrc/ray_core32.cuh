@@ -1,11 +1,12 @@
-// Ray stepper v2 for sm_100a: FP64 master state, FP32 cell-relative RHS, register cell cache,
-// packed FP32x2 (FFMA2/FMUL2) trilinear arithmetic.
+// Ray stepper v3 for sm_100a: FP64 master state, FP32 cell-relative RHS, register cell cache held
+// as the cell's trilinear POLYNOMIAL, packed FP32x2 (FFMA2) evaluation, one RHS body in the binary.
 //
-// Same mathematics as ray_integrator.cuh (build_rays.py:158-239) reorganised around what the
-// first ncu capture showed (profiles/r1a_trace_rays_kernel_*.txt): the FP64 stepper issues ~2500
-// instructions per ray-step at 49 % issue utilisation, with the L1 data pipe at 65 % (8 x LDG.128
-// per RHS, 9.3 wavefronts each), the FP64 pipe at 29 % and the XU pipe (f64<->f32/int
-// conversions, MUFU) at 29 %.
+// Same mathematics as ray_integrator.cuh (build_rays.py:158-239) reorganised around what ncu showed.
+// profiles/r1a_trace_rays_kernel_*.txt (FP64 stepper): ~2500 instructions per ray-step at 49 %
+// issue utilisation, L1 data pipe 65 % (8 x LDG.128 per RHS), FP64 pipe 29 %, XU pipe 29 %.
+// profiles/r1d_render_map_kernel_c4_bench.txt (stepper v2, RK4 stages and EDGE/interior variants
+// all inlined: 16 copies of the RHS, 134 KB of SASS): 30 % of all stall samples are `no_inst` —
+// the 32 KB instruction cache thrashes — and 4 % of the instructions are local-memory spills.
 //
 //  * The ray's position and wave vector stay FP64 (the "master" state): every step adds
 //    (double)sum * (dt/6 * C_R), so the accumulation over thousands of steps is exact to 1e-16
@@ -16,23 +17,32 @@
 //    a step could span a whole cell).  Cell fractions carry 6e-8 of a cell (~1e-9 R_sun), the
 //    corners are FP32 anyway, omega = sqrt(w^2+k^2) and the derivatives need 1e-7 relative:
 //    increments are ~1e-3 R_sun, so the per-step error is ~1e-10 R_sun and random.
-//  * The 8 corners of the current cell (32 floats) live in registers; a stage whose cell differs
-//    from the cached one re-fetches with predicated LDG.128 (only the lanes that moved generate
-//    L1 wavefronts).  A ray spends ~10 steps x 12 RHS evaluations in one cell.
-//  * The four channels {omega_pe, d/dx, d/dy, d/dz} of a corner are two aligned float2 pairs, so
-//    the 28 scalar lerps of a trilinear gather become 14 packed lerps = FMUL2 + FFMA2
-//    (Blackwell's packed FP32x2 pipe): half the issue slots.
+//  * The current cell lives in 32 registers as the coefficients of its trilinear polynomial
+//        f = (a0 + az z) + y (ay + ayz z) + x ((ax + axz z) + y (axy + axyz z))
+//    for the channel pairs {omega_pe, d/dx} and {d/dy, d/dz}: one RHS is 14 packed FFMA2 with a
+//    dependency depth of 3 (the nested-lerp form is 14 FMUL2 + 14 FFMA2, depth 6).  A stage whose
+//    cell differs from the cached one re-fetches the 8 corners with LDG.128 (only the lanes that
+//    moved generate L1 wavefronts) and differences them once (24 FADD2).  A ray spends ~10-35
+//    steps x up to 12 RHS evaluations in one cell.
+//  * ONE copy of the RHS in the binary: the 4 RK4 stages and the 3 rays of a step (central + the
+//    two pencil rays) are rolled loops around it, and the face handling is a run-time flag
+//    instead of a template variant, so the whole stepper is ~600 instructions (< 10 KB) and the
+//    hot loop of the fused kernel fits the instruction cache.
 //  * Away from the cube faces no stage can leave the cube, so the per-stage bounds test is
-//    hoisted to one test of the base cell per step (EDGE path only near the faces).
+//    one test of the base cell per step (`edge`); the exact scipy bounds run near the faces only.
 #pragma once
 
 #include "ray_integrator.cuh"
 
 namespace rtgrff {
 
+// The cached cell: element offset of its (i,j,k) corner (-1 = empty), its integer coordinates and
+// the polynomial coefficients of the channel pairs L = {omega_pe, d/dx}, H = {d/dy, d/dz}.
 struct Cell {
-    int off;  // element offset of corner (i,j,k); -1 = empty
-    float4 c000, c001, c010, c011, c100, c101, c110, c111;
+    int off;
+    int ci, cj, ck;
+    float2 l0, lz, ly, lyz, lx, lxz, lxy, lxyz;
+    float2 h0, hz, hy, hyz, hx, hxz, hxy, hxyz;
 };
 
 struct Deriv32 {
@@ -40,66 +50,109 @@ struct Deriv32 {
     float gx, gy, gz;   // (omega_pe/omega) * grad omega_pe   (dk/dt = -C_R * g)
 };
 
-__device__ __forceinline__ float2 lerp2(float2 a, float2 b, float2 u, float2 t)
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+
+// Fetch the 8 corners of the cell at element offset `off` and turn them into polynomial coefficients.
+__device__ __forceinline__ void load_cell(const RayCube &C, int off, Cell &c)
 {
-    return __ffma2_rn(b, t, __fmul2_rn(a, u));   // a*(1-t) + b*t on both halves
+    const float4 *p = C.c + off;
+    const float4 c000 = __ldg(p), c001 = __ldg(p + 1);
+    const float4 c010 = __ldg(p + C.sy), c011 = __ldg(p + C.sy + 1);
+    const float4 c100 = __ldg(p + C.sx), c101 = __ldg(p + C.sx + 1);
+    const float4 c110 = __ldg(p + C.sx + C.sy), c111 = __ldg(p + C.sx + C.sy + 1);
+    c.off = off;
+#define RT_POLY(LO, a0, az, ay, ayz, ax, axz, axy, axyz)                                          \
+    {                                                                                             \
+        const float2 d00 = sub2(LO(c001), LO(c000)), d01 = sub2(LO(c011), LO(c010));              \
+        const float2 d10 = sub2(LO(c101), LO(c100)), d11 = sub2(LO(c111), LO(c110));              \
+        const float2 y0 = sub2(LO(c010), LO(c000)), y1 = sub2(LO(c110), LO(c100));                \
+        const float2 yz0 = sub2(d01, d00), yz1 = sub2(d11, d10);                                  \
+        c.a0 = LO(c000); c.az = d00; c.ay = y0; c.ayz = yz0;                                      \
+        c.ax = sub2(LO(c100), LO(c000)); c.axz = sub2(d10, d00);                                  \
+        c.axy = sub2(y1, y0); c.axyz = sub2(yz1, yz0);                                            \
+    }
+#define RT_LO(c) make_float2((c).x, (c).y)
+#define RT_HI(c) make_float2((c).z, (c).w)
+    RT_POLY(RT_LO, l0, lz, ly, lyz, lx, lxz, lxy, lxyz)
+    RT_POLY(RT_HI, h0, hz, hy, hyz, hx, hxz, hxy, hxyz)
+#undef RT_POLY
+#undef RT_LO
+#undef RT_HI
 }
 
-// One RHS evaluation at cell-relative position p (cell units, -1 <= p < 2) of base cell (bi,bj,bk).
-template <bool EDGE>
-__device__ __forceinline__ Deriv32 rhs32(const RayCube &C, int bi, int bj, int bk, int base_off, Cell &cache, float px,
-                                         float py, float pz, float kx, float ky, float kz)
+// 0 <= t < 1 as one unsigned compare on the bit pattern (negative, NaN and -0 fail).
+__device__ __forceinline__ bool in_unit(float t) { return __float_as_uint(t) < 0x3f800000u; }
+
+// Slow path of an RHS evaluation: the point (tx,ty,tz) — coordinates relative to the cached cell —
+// lies outside it.  Moves the cache to the cell that holds the point (scipy bounds
+// g[0] <= x <= g[n-1]; the last node belongs to cell n-2 with t = 1), rebases the step's base
+// position (px,py,pz) and the point onto the new cell.  Returns false, leaving everything
+// untouched, when the point is outside the cube or not a number: that stage contributes a zero
+// derivative (build_rays.py:169-174).
+__device__ __forceinline__ bool move_cell(const RayCube &C, Cell &c, float &px, float &py, float &pz, float &tx,
+                                          float &ty, float &tz)
+{
+    float fx = floorf(tx), fy = floorf(ty), fz = floorf(tz);
+    if (!((fx + fy) + fz == (fx + fy) + fz)) return false;                    // NaN coordinate
+    int ni = c.ci + (int)fx, nj = c.cj + (int)fy, nk = c.ck + (int)fz;
+    float ux = tx - fx, uy = ty - fy, uz = tz - fz;
+    if (ni == C.nx - 1 && ux == 0.0f) { ni = C.nx - 2; ux = 1.0f; fx -= 1.0f; }
+    if (nj == C.ny - 1 && uy == 0.0f) { nj = C.ny - 2; uy = 1.0f; fy -= 1.0f; }
+    if (nk == C.nz - 1 && uz == 0.0f) { nk = C.nz - 2; uz = 1.0f; fz -= 1.0f; }
+    if ((unsigned)ni > (unsigned)(C.nx - 2) || (unsigned)nj > (unsigned)(C.ny - 2) ||
+        (unsigned)nk > (unsigned)(C.nz - 2))
+        return false;
+    const int off = (ni * C.ny + nj) * C.nz + nk;
+    if (off != c.off) load_cell(C, off, c);
+    c.ci = ni; c.cj = nj; c.ck = nk;
+    px -= fx; py -= fy; pz -= fz;
+    tx = ux; ty = uy; tz = uz;
+    return true;
+}
+
+// One RHS evaluation at p + d, all in cell units relative to the CACHED cell: p is the step's base
+// position (rebased when the cache moves), d the offset of this stage of this ray from it.  The
+// common case — the point is inside the cached cell — costs one range test; the cell change, the
+// bounds of the cube and the re-fetch all live on the slow path.
+__device__ __forceinline__ Deriv32 rhs32(const RayCube &C, Cell &cache, float &px, float &py, float &pz, float dx,
+                                         float dy, float dz, float kx, float ky, float kz)
 {
     Deriv32 d;
     d.vx = d.vy = d.vz = d.gx = d.gy = d.gz = 0.0f;
-    const bool hx = px >= 1.0f, lx = px < 0.0f, hy = py >= 1.0f, ly = py < 0.0f, hz = pz >= 1.0f, lz = pz < 0.0f;
-    float tx = px, ty = py, tz = pz;
-    tx = hx ? tx - 1.0f : tx; tx = lx ? tx + 1.0f : tx;
-    ty = hy ? ty - 1.0f : ty; ty = ly ? ty + 1.0f : ty;
-    tz = hz ? tz - 1.0f : tz; tz = lz ? tz + 1.0f : tz;
-    int off;
-    if (EDGE) {
-        // scipy bounds per stage: g[0] <= x <= g[n-1]; the last node belongs to cell n-2 with t = 1
-        int ci = bi + (int)hx - (int)lx, cj = bj + (int)hy - (int)ly, ck = bk + (int)hz - (int)lz;
-        if (ci == C.nx - 1 && tx == 0.0f) { ci = C.nx - 2; tx = 1.0f; }
-        if (cj == C.ny - 1 && ty == 0.0f) { cj = C.ny - 2; ty = 1.0f; }
-        if (ck == C.nz - 1 && tz == 0.0f) { ck = C.nz - 2; tz = 1.0f; }
-        if ((unsigned)ci > (unsigned)(C.nx - 2) || (unsigned)cj > (unsigned)(C.ny - 2) ||
-            (unsigned)ck > (unsigned)(C.nz - 2))
-            return d;
-        off = (ci * C.ny + cj) * C.nz + ck;
-    } else {
-        off = base_off;
-        off = hx ? off + C.sx : off; off = lx ? off - C.sx : off;
-        off = hy ? off + C.sy : off; off = ly ? off - C.sy : off;
-        off = hz ? off + 1 : off;    off = lz ? off - 1 : off;
+    float tx = px + dx, ty = py + dy, tz = pz + dz;
+#define RT_EVAL_POLY(wg, gg)                                                                                    \
+    {                                                                                                           \
+        const float2 tz2 = make_float2(tz, tz), ty2 = make_float2(ty, ty), tx2 = make_float2(tx, tx);           \
+        /* {omega_pe, d/dx} */                                                                                  \
+        wg = __ffma2_rn(                                                                                        \
+            __ffma2_rn(__ffma2_rn(cache.lxyz, tz2, cache.lxy), ty2, __ffma2_rn(cache.lxz, tz2, cache.lx)), tx2, \
+            __ffma2_rn(__ffma2_rn(cache.lyz, tz2, cache.ly), ty2, __ffma2_rn(cache.lz, tz2, cache.l0)));        \
+        /* {d/dy, d/dz} */                                                                                      \
+        gg = __ffma2_rn(                                                                                        \
+            __ffma2_rn(__ffma2_rn(cache.hxyz, tz2, cache.hxy), ty2, __ffma2_rn(cache.hxz, tz2, cache.hx)), tx2, \
+            __ffma2_rn(__ffma2_rn(cache.hyz, tz2, cache.hy), ty2, __ffma2_rn(cache.hz, tz2, cache.h0)));        \
     }
-    if (off != cache.off) {
-        const float4 *p = C.c + off;
-        cache.c000 = __ldg(p); cache.c001 = __ldg(p + 1);
-        cache.c010 = __ldg(p + C.sy); cache.c011 = __ldg(p + C.sy + 1);
-        cache.c100 = __ldg(p + C.sx); cache.c101 = __ldg(p + C.sx + 1);
-        cache.c110 = __ldg(p + C.sx + C.sy); cache.c111 = __ldg(p + C.sx + C.sy + 1);
-        cache.off = off;
+    float2 wg, gg;
+#ifdef RT_SPECULATE
+    // evaluate on the cached cell before the range test resolves; the slow path re-evaluates
+    RT_EVAL_POLY(wg, gg)
+    if (!(in_unit(tx) & in_unit(ty) & in_unit(tz))) {
+        if (!move_cell(C, cache, px, py, pz, tx, ty, tz)) return d;
+        RT_EVAL_POLY(wg, gg)
     }
-    const float2 tz2 = make_float2(tz, tz), uz2 = make_float2(1.0f - tz, 1.0f - tz);
-    const float2 ty2 = make_float2(ty, ty), uy2 = make_float2(1.0f - ty, 1.0f - ty);
-    const float2 tx2 = make_float2(tx, tx), ux2 = make_float2(1.0f - tx, 1.0f - tx);
-#define RT_LO(c) make_float2((c).x, (c).y)
-#define RT_HI(c) make_float2((c).z, (c).w)
-#define RT_TRI2(H)                                                                                          \
-    lerp2(lerp2(lerp2(H(cache.c000), H(cache.c001), uz2, tz2), lerp2(H(cache.c010), H(cache.c011), uz2, tz2), uy2, ty2), \
-          lerp2(lerp2(H(cache.c100), H(cache.c101), uz2, tz2), lerp2(H(cache.c110), H(cache.c111), uz2, tz2), uy2, ty2), ux2, tx2)
-    const float2 wg = RT_TRI2(RT_LO);   // {omega_pe, d/dx}
-    const float2 gg = RT_TRI2(RT_HI);   // {d/dy, d/dz}
-#undef RT_TRI2
-#undef RT_LO
-#undef RT_HI
+#else
+    if (!(in_unit(tx) & in_unit(ty) & in_unit(tz))) {
+        if (!move_cell(C, cache, px, py, pz, tx, ty, tz)) return d;
+    }
+    RT_EVAL_POLY(wg, gg)
+#endif
+#undef RT_EVAL_POLY
     const float w = wg.x;
     const float om2 = fmaf(w, w, fmaf(kx, kx, fmaf(ky, ky, kz * kz)));
     // valid = isfinite(omega_pe) & isfinite(omega) & (omega > 0)   (build_rays.py:169); a non-finite
-    // omega_pe or k makes omega^2 non-finite, so one range test on omega^2 covers all three
-    if (!(om2 > 0.0f) || !(om2 < INFINITY)) return d;
+    // omega_pe or k makes omega^2 non-finite, so one range test on omega^2 covers all three:
+    // 0 < omega^2 < inf  <=>  bit pattern in [1, 0x7f7fffff]
+    if (__float_as_uint(om2) - 1u >= 0x7f7fffffu) return d;
     float inv_om;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv_om) : "f"(om2));   // MUFU.RSQ, 2 ulp; omega^2 ~ 1e17
     const float a = w * inv_om;
@@ -118,7 +171,7 @@ struct StepConst {
     float perturb;
 };
 
-__device__ __forceinline__ StepConst make_step_const(const RayCube &C, double dt, double perturb_ratio)
+__host__ __device__ __forceinline__ StepConst make_step_const(const RayCube &C, double dt, double perturb_ratio)
 {
     StepConst k;
     const double h = 0.5 * dt * kC_R;
@@ -139,96 +192,92 @@ inline double max_stage_offset_cells(double dt, double perturb_ratio, double idx
     return (1.0 + fabs(perturb_ratio)) * dt * kC_R * i;
 }
 
-struct RkSum {
-    float vx, vy, vz, gx, gy, gz;
-};
-
-// Classic RK4 (build_rays.py:177-182) in cell-relative FP32: returns sum = k1 + 2 k2 + 2 k3 + k4.
-template <bool EDGE>
-__device__ __forceinline__ RkSum rk4_32(const RayCube &C, const StepConst &K, int bi, int bj, int bk, int base_off,
-                                        Cell &cache, float px, float py, float pz, float kx, float ky, float kz)
-{
-    const Deriv32 k1 = rhs32<EDGE>(C, bi, bj, bk, base_off, cache, px, py, pz, kx, ky, kz);
-    const Deriv32 k2 = rhs32<EDGE>(C, bi, bj, bk, base_off, cache, fmaf(K.hx, k1.vx, px), fmaf(K.hy, k1.vy, py),
-                                   fmaf(K.hz, k1.vz, pz), fmaf(-K.hk, k1.gx, kx), fmaf(-K.hk, k1.gy, ky),
-                                   fmaf(-K.hk, k1.gz, kz));
-    const Deriv32 k3 = rhs32<EDGE>(C, bi, bj, bk, base_off, cache, fmaf(K.hx, k2.vx, px), fmaf(K.hy, k2.vy, py),
-                                   fmaf(K.hz, k2.vz, pz), fmaf(-K.hk, k2.gx, kx), fmaf(-K.hk, k2.gy, ky),
-                                   fmaf(-K.hk, k2.gz, kz));
-    const float fx = 2.0f * K.hx, fy = 2.0f * K.hy, fz = 2.0f * K.hz, fk = 2.0f * K.hk;
-    const Deriv32 k4 = rhs32<EDGE>(C, bi, bj, bk, base_off, cache, fmaf(fx, k3.vx, px), fmaf(fy, k3.vy, py),
-                                   fmaf(fz, k3.vz, pz), fmaf(-fk, k3.gx, kx), fmaf(-fk, k3.gy, ky),
-                                   fmaf(-fk, k3.gz, kz));
-    RkSum s;
-    s.vx = fmaf(2.0f, k2.vx, k1.vx) + fmaf(2.0f, k3.vx, k4.vx);
-    s.vy = fmaf(2.0f, k2.vy, k1.vy) + fmaf(2.0f, k3.vy, k4.vy);
-    s.vz = fmaf(2.0f, k2.vz, k1.vz) + fmaf(2.0f, k3.vz, k4.vz);
-    s.gx = fmaf(2.0f, k2.gx, k1.gx) + fmaf(2.0f, k3.gx, k4.gx);
-    s.gy = fmaf(2.0f, k2.gy, k1.gy) + fmaf(2.0f, k3.gy, k4.gy);
-    s.gz = fmaf(2.0f, k2.gz, k1.gz) + fmaf(2.0f, k3.gz, k4.gz);
-    return s;
-}
-
-template <bool CS, bool EDGE>
-__device__ __forceinline__ void step32_body(const RayCube &C, const StepConst &K, Cell &cache, State &s, int bi, int bj,
-                                            int bk, float px, float py, float pz, bool want_s, double &s_step)
-{
-    const int base_off = (bi * C.ny + bj) * C.nz + bk;
-    const float kx = (float)s.kx, ky = (float)s.ky, kz = (float)s.kz;
-    const RkSum c = rk4_32<EDGE>(C, K, bi, bj, bk, base_off, cache, px, py, pz, kx, ky, kz);
-    s.rx = fma((double)c.vx, K.c6, s.rx); s.ry = fma((double)c.vy, K.c6, s.ry); s.rz = fma((double)c.vz, K.c6, s.rz);
-    s.kx = fma((double)c.gx, -K.c6, s.kx); s.ky = fma((double)c.gy, -K.c6, s.ky); s.kz = fma((double)c.gz, -K.c6, s.kz);
-    if (CS && want_s) {
-        // build_rays.py:209-239 with d = r_pert' - r_central' = eps*e + c6*(sum_v_pert - sum_v_central)
-        const float dx = K.c6r * c.vx, dy = K.c6r * c.vy, dz = K.c6r * c.vz;
-        const float nrd = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
-        const float inv = 1.0f / (nrd + 1e-32f);
-        const float tx = dx * inv, ty = dy * inv, tz = dz * inv;
-        const bool use_z = fabsf(tz) < 0.9f;
-        float e1x = use_z ? -ty : tz, e1y = use_z ? tx : 0.0f, e1z = use_z ? 0.0f : -tx;
-        const float n1 = 1.0f / (sqrtf(fmaf(e1x, e1x, fmaf(e1y, e1y, e1z * e1z))) + 1e-30f);
-        e1x *= n1; e1y *= n1; e1z *= n1;
-        float e2x = ty * e1z - tz * e1y, e2y = tz * e1x - tx * e1z, e2z = tx * e1y - ty * e1x;
-        const float n2 = 1.0f / (sqrtf(fmaf(e2x, e2x, fmaf(e2y, e2y, e2z * e2z))) + 1e-30f);
-        e2x *= n2; e2y *= n2; e2z *= n2;
-        const float eps = K.perturb * nrd;
-        float d1x = 0.f, d1y = 0.f, d1z = 0.f, d2x = 0.f, d2y = 0.f, d2z = 0.f;
-        // the two pencil rays share one code body (keeps the kernel inside the instruction cache)
-#ifdef RT_PENCIL_UNROLL
-#pragma unroll
-#else
-#pragma unroll 1
-#endif
-        for (int q = 0; q < 2; ++q) {
-            const float ex = eps * (q ? e2x : e1x), ey = eps * (q ? e2y : e1y), ez = eps * (q ? e2z : e1z);
-            const RkSum a = rk4_32<EDGE>(C, K, bi, bj, bk, base_off, cache, fmaf(ex, K.ix, px), fmaf(ey, K.iy, py),
-                                         fmaf(ez, K.iz, pz), kx, ky, kz);
-            const float ddx = fmaf(K.c6r, a.vx - c.vx, ex), ddy = fmaf(K.c6r, a.vy - c.vy, ey),
-                        ddz = fmaf(K.c6r, a.vz - c.vz, ez);
-            if (q) { d2x = ddx; d2y = ddy; d2z = ddz; } else { d1x = ddx; d1y = ddy; d1z = ddz; }
-        }
-        const float cx = d1y * d2z - d1z * d2y, cy = d1z * d2x - d1x * d2z, cz = d1x * d2y - d1y * d2x;
-        s_step = (double)(fabsf(fmaf(cx, tx, fmaf(cy, ty, cz * tz))) / (eps * eps));
-    }
-}
-
-// One full step of the master state `s` (which must be inside the cube): central RK4 and, when
-// `want_s` (warp-uniform), the cross-section ratio of this step.  Returns true if the state changed.
+// One full step of the master state `s`: classic RK4 (build_rays.py:177-182) of the central ray
+// and, when `want_s` (warp-uniform), the same RK4 on the two pencil rays displaced by eps along
+// (e1, e2) _|_ t_hat with the cross-section ratio of this step (build_rays.py:209-239, with
+// d = r_pert' - r_central' = eps*e + c6*(sum_v_pert - sum_v_central)).  Returns false when the ray
+// is frozen: outside the cube / NaN, or every stage derivative exactly zero (the reference's
+// update is then exactly zero too, for ever).
 template <bool CS>
 __device__ __forceinline__ bool step32(const RayCube &C, const StepConst &K, Cell &cache, State &s, bool want_s,
                                        double &s_step)
 {
-    // split the master position into base cell + fraction (FP64 -> FP32 once per step)
     const double fx = (s.rx - C.x0) * C.idx, fy = (s.ry - C.y0) * C.idy, fz = (s.rz - C.z0) * C.idz;
-    const int bi = min((int)fx, C.nx - 2), bj = min((int)fy, C.ny - 2), bk = min((int)fz, C.nz - 2);
-    const float px = (float)(fx - (double)bi), py = (float)(fy - (double)bj), pz = (float)(fz - (double)bk);
-    const State s0 = s;
-    // stages and pencil rays stay within one cell of the base cell: only a base cell next to a face
-    // can produce an out-of-cube stage
-    const bool edge = (bi < 1) | (bi > C.nx - 3) | (bj < 1) | (bj > C.ny - 3) | (bk < 1) | (bk > C.nz - 3);
-    if (edge) step32_body<CS, true>(C, K, cache, s, bi, bj, bk, px, py, pz, want_s, s_step);
-    else step32_body<CS, false>(C, K, cache, s, bi, bj, bk, px, py, pz, want_s, s_step);
-    return state_differs(s, s0);
+    if (cache.off < 0) {
+        // first step of this ray: cache the cell of the start position
+        if (!in_cube(C, s.rx, s.ry, s.rz)) return false;
+        cache.ci = min((int)fx, C.nx - 2); cache.cj = min((int)fy, C.ny - 2); cache.ck = min((int)fz, C.nz - 2);
+        load_cell(C, (cache.ci * C.ny + cache.cj) * C.nz + cache.ck, cache);
+    }
+    // a step moves the ray by less than one cell and the cached cell is the cell of the last stage
+    // evaluated, so the master position is within two cells of it: it can only be outside the cube
+    // when the cached cell is that close to a face (exact scipy test there; a frozen ray stays here)
+    const bool edge = (cache.ci < 2) | (cache.ci > C.nx - 4) | (cache.cj < 2) | (cache.cj > C.ny - 4) |
+                      (cache.ck < 2) | (cache.ck > C.nz - 4);
+    if (edge && !in_cube(C, s.rx, s.ry, s.rz)) return false;
+    // master position relative to the cached cell (FP64 -> FP32 once per step)
+    float px = (float)(fx - (double)cache.ci), py = (float)(fy - (double)cache.cj), pz = (float)(fz - (double)cache.ck);
+    const float kx = (float)s.kx, ky = (float)s.ky, kz = (float)s.kz;
+    const int n_rays = (CS && want_s) ? 3 : 1;
+    float ox = 0.0f, oy = 0.0f, oz = 0.0f;          // displacement of the current ray from the central one, R_sun
+    float cvx = 0.0f, cvy = 0.0f, cvz = 0.0f;       // central ray: sum of v over the stages
+    float tx = 0.0f, ty = 0.0f, tz = 0.0f, e2x = 0.0f, e2y = 0.0f, e2z = 0.0f, eps = 0.0f;
+    float d1x = 0.0f, d1y = 0.0f, d1z = 0.0f;
+    bool moved = false;
+#pragma unroll 1
+    for (int q = 0; q < n_rays; ++q) {
+        const float qx = ox * K.ix, qy = oy * K.iy, qz = oz * K.iz;    // start of this ray relative to p, cells
+        float dx = qx, dy = qy, dz = qz, skx = kx, sky = ky, skz = kz;
+        float avx = 0.0f, avy = 0.0f, avz = 0.0f, agx = 0.0f, agy = 0.0f, agz = 0.0f;   // k1 + 2 k2 + 2 k3 + k4
+#ifdef RT_STAGE_ROLLED
+#pragma unroll 1
+#else
+#pragma unroll
+#endif
+        for (int st = 0; st < 4; ++st) {
+            const Deriv32 d = rhs32(C, cache, px, py, pz, dx, dy, dz, skx, sky, skz);
+            const float w = (st == 0 || st == 3) ? 1.0f : 2.0f;
+            avx = fmaf(w, d.vx, avx); avy = fmaf(w, d.vy, avy); avz = fmaf(w, d.vz, avz);
+            agx = fmaf(w, d.gx, agx); agy = fmaf(w, d.gy, agy); agz = fmaf(w, d.gz, agz);
+            const float a = (st < 2) ? 1.0f : 2.0f;   // stages 2, 3 at dt/2, stage 4 at dt (K.h* are half steps)
+            dx = fmaf(a * K.hx, d.vx, qx); dy = fmaf(a * K.hy, d.vy, qy); dz = fmaf(a * K.hz, d.vz, qz);
+            const float ak = -a * K.hk;
+            skx = fmaf(ak, d.gx, kx); sky = fmaf(ak, d.gy, ky); skz = fmaf(ak, d.gz, kz);
+        }
+        if (q == 0) {
+            moved = (fabsf(avx) + fabsf(avy) + fabsf(avz) + fabsf(agx) + fabsf(agy) + fabsf(agz)) != 0.0f;
+            s.kx = fma((double)agx, -K.c6, s.kx); s.ky = fma((double)agy, -K.c6, s.ky); s.kz = fma((double)agz, -K.c6, s.kz);
+            s.rx = fma((double)avx, K.c6, s.rx); s.ry = fma((double)avy, K.c6, s.ry); s.rz = fma((double)avz, K.c6, s.rz);
+            cvx = avx; cvy = avy; cvz = avz;
+            if (n_rays > 1) {
+                const float dx = K.c6r * cvx, dy = K.c6r * cvy, dz = K.c6r * cvz;
+                const float nrd = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+                const float inv = 1.0f / (nrd + 1e-32f);
+                tx = dx * inv; ty = dy * inv; tz = dz * inv;
+                // reference axis: z if |t_z| < 0.9 else y (build_rays.py:188-194); e1 = a x t, e2 = t x e1
+                const bool use_z = fabsf(tz) < 0.9f;
+                float e1x = use_z ? -ty : tz, e1y = use_z ? tx : 0.0f, e1z = use_z ? 0.0f : -tx;
+                const float n1 = 1.0f / (sqrtf(fmaf(e1x, e1x, fmaf(e1y, e1y, e1z * e1z))) + 1e-30f);
+                e1x *= n1; e1y *= n1; e1z *= n1;
+                e2x = ty * e1z - tz * e1y; e2y = tz * e1x - tx * e1z; e2z = tx * e1y - ty * e1x;
+                const float n2 = 1.0f / (sqrtf(fmaf(e2x, e2x, fmaf(e2y, e2y, e2z * e2z))) + 1e-30f);
+                e2x *= n2; e2y *= n2; e2z *= n2;
+                eps = K.perturb * nrd;
+                ox = eps * e1x; oy = eps * e1y; oz = eps * e1z;
+            }
+        } else {
+            const float ddx = fmaf(K.c6r, avx - cvx, ox), ddy = fmaf(K.c6r, avy - cvy, oy),
+                        ddz = fmaf(K.c6r, avz - cvz, oz);
+            if (q == 1) {
+                d1x = ddx; d1y = ddy; d1z = ddz;
+                ox = eps * e2x; oy = eps * e2y; oz = eps * e2z;
+            } else {
+                const float cx = d1y * ddz - d1z * ddy, cy = d1z * ddx - d1x * ddz, cz = d1x * ddy - d1y * ddx;
+                s_step = (double)(fabsf(fmaf(cx, tx, fmaf(cy, ty, cz * tz))) / (eps * eps));
+            }
+        }
+    }
+    return moved;
 }
 
 }  // namespace rtgrff

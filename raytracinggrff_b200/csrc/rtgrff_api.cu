@@ -437,6 +437,7 @@ int rtgrff_trace(rtgrff_ctx *c, int64_t n_rays, const double *x_start, const dou
     a.kvec = kvec ? c->in3.as<double>() : nullptr;
     a.omega0 = 2.0 * M_PI * freq_hz;
     a.dt = dt; a.perturb_ratio = perturb_ratio;
+    a.K = make_step_const(a.cube, dt, perturb_ratio);
     a.n_steps = n_steps; a.stride = record_stride; a.n_rec = n_rec;
     a.s_mode = s_mode;
     a.cs_every_step = cs_every_step();
@@ -645,6 +646,7 @@ int rtgrff_render_map(rtgrff_ctx *c, int64_t n_rays, const double *x_start, cons
     if (n_rays > 0 && (!x_start || !y_start || !z_start)) return fail(RTGRFF_EINVAL, "null start arrays");
     if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
     if (n_rays == 0) return RTGRFF_OK;
+    const RayCube rc = ray_cube_of(c);
     std::vector<FreqDev> fd(n_freq);
     int64_t nominal = 0;
     for (int f = 0; f < n_freq; ++f) {
@@ -655,6 +657,8 @@ int rtgrff_render_map(rtgrff_ctx *c, int64_t n_rays, const double *x_start, cons
         fd[f].dt = freqs[f].dt;
         fd[f].n_steps = freqs[f].n_steps;
         fd[f].stride = freqs[f].record_stride;
+        fd[f].K = make_step_const(rc, freqs[f].dt, perturb_ratio);
+        fd[f].fq = make_freq(freqs[f].freq_hz);
         nominal += freqs[f].n_steps * n_rays;
     }
     const size_t nb = (size_t)n_rays * sizeof(double);
@@ -666,10 +670,8 @@ int rtgrff_render_map(rtgrff_ctx *c, int64_t n_rays, const double *x_start, cons
         if (n_rays >= ((int64_t)1 << 31)) return fail(RTGRFF_EINVAL, "ray_order needs n_rays < 2^31");
         RT_TRY(h2d(c, c->out2, ray_order, (size_t)n_rays * sizeof(int32_t)));
     }
-    RT_TRY(c->counters.reserve(64 + (size_t)n_freq * sizeof(FreqDev)));
+    RT_TRY(c->counters.reserve(64));
     RT_CUDA(cudaMemsetAsync(c->counters.p, 0, 64, c->stream));
-    FreqDev *dfreq = reinterpret_cast<FreqDev *>(c->counters.as<char>() + 64);
-    RT_CUDA(cudaMemcpyAsync(dfreq, fd.data(), (size_t)n_freq * sizeof(FreqDev), cudaMemcpyHostToDevice, c->stream));
     double *dtb = tb, *dvi = vi;
     if (!out_on_device) {
         RT_TRY(c->out0.reserve((size_t)n_freq * nb));
@@ -677,7 +679,7 @@ int rtgrff_render_map(rtgrff_ctx *c, int64_t n_rays, const double *x_start, cons
         dtb = c->out0.as<double>(); dvi = c->out1.as<double>();
     }
     MapArgs a;
-    a.cube = ray_cube_of(c);
+    a.cube = rc;
     a.fcube = c->fcube.as<float4>();
     a.bcube = c->has_bvec ? c->bcube.as<float4>() : nullptr;
     a.fg = c->fgeomf;
@@ -685,14 +687,13 @@ int rtgrff_render_map(rtgrff_ctx *c, int64_t n_rays, const double *x_start, cons
     a.x_start = c->in0.as<double>(); a.y_start = c->in1.as<double>(); a.z_start = c->in2.as<double>();
     a.kvec = kvec ? c->in3.as<double>() : nullptr;
     a.ray_order = ray_order ? c->out2.as<int>() : nullptr;
-    a.n_freq = n_freq; a.freqs = dfreq;
     a.perturb_ratio = perturb_ratio; a.area = pixel_area_cm2;
     a.r_sun_cm = (float)r_sun_cm; a.fill_ne = 0.0f; a.fill_te = 1e4f; a.fill_b = 0.0f;
     a.em_flag = em_flag; a.s_max = s_max; a.use_bvec = use_bvec; a.order = voxel_order;
     a.cs_every_step = cs_every_step();
     a.tb = dtb; a.vi = dvi;
     a.active_steps = c->counters.as<unsigned long long>();
-    const dim3 grid(blocks_for(n_rays, RT_BLOCK), (unsigned int)n_freq), block(RT_BLOCK);
+    const dim3 block(RT_BLOCK);
     const bool gr = !(em_flag & 1);
     RT_CUDA(cudaEventRecord(c->ev0, c->stream));
     const int variant = (trace_cs ? 8 : 0) | (voxel_order == RTGRFF_ORDER_REVERSED ? 4 : 0) | (use_bvec ? 2 : 0) | (gr ? 1 : 0);
@@ -706,6 +707,12 @@ int rtgrff_render_map(rtgrff_ctx *c, int64_t n_rays, const double *x_start, cons
         if (!(max_stage_offset_cells(freqs[f].dt, trace_cs ? perturb_ratio : 0.0, c->wgeom.idx, c->wgeom.idy,
                                      c->wgeom.idz) < 0.999))
             mode = MODE_F64;
+    // the per-frequency constants travel in the kernel parameters: kMaxFreqPerLaunch frequencies per launch
+    for (int f0 = 0; f0 < n_freq; f0 += kMaxFreqPerLaunch) {
+    a.freq_base = f0;
+    a.n_freq = n_freq - f0 < kMaxFreqPerLaunch ? n_freq - f0 : kMaxFreqPerLaunch;
+    for (int f = 0; f < a.n_freq; ++f) a.freqs[f] = fd[f0 + f];
+    const dim3 grid(blocks_for(n_rays, RT_BLOCK), (unsigned int)a.n_freq);
     switch (variant) {
         RT_MAP_CASE(0, false, 0, false, false) RT_MAP_CASE(1, false, 0, false, true)
         RT_MAP_CASE(2, false, 0, true, false) RT_MAP_CASE(3, false, 0, true, true)
@@ -716,8 +723,9 @@ int rtgrff_render_map(rtgrff_ctx *c, int64_t n_rays, const double *x_start, cons
         RT_MAP_CASE(12, true, 1, false, false) RT_MAP_CASE(13, true, 1, false, true)
         RT_MAP_CASE(14, true, 1, true, false) RT_MAP_CASE(15, true, 1, true, true)
     }
-#undef RT_MAP_CASE
     RT_TRY(launched(c, "render_map_kernel"));
+    }
+#undef RT_MAP_CASE
     RT_CUDA(cudaEventRecord(c->ev1, c->stream));
     c->ev_valid = true;
     if (!out_on_device) {

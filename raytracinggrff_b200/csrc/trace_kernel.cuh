@@ -25,8 +25,7 @@ __device__ __forceinline__ bool advance_ray(const RayCube &C, const StepConst &K
 {
     bool moved;
     if (MODE == MODE_FAST32) {
-        moved = in_cube(C, s.rx, s.ry, s.rz);
-        if (moved) moved = step32<CS>(C, K, cache, s, want_s, s_step);
+        moved = step32<CS>(C, K, cache, s, want_s, s_step);
     } else {
         constexpr bool L64 = (MODE == MODE_F64_LERP64);
         const State s0 = s;
@@ -44,6 +43,7 @@ struct TraceArgs {
     const double *x_start, *y_start, *z_start;  // device, (n_rays)
     const double *kvec;                          // device, (n_rays,3) or nullptr -> (0,0,-1)
     double omega0, dt, perturb_ratio;
+    StepConst K;                                 // host-prepared constants of the FP32 stepper (constant bank)
     int64_t n_steps, stride, n_rec;
     int s_mode;
     int cs_every_step;   // 1: trace the pencil rays at every step even when only recorded steps are kept
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_MINB) trace_rays_kernel(const Tra
     const int64_t ray = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool has_ray = ray < a.n_rays;
     const RayCube &C = a.cube;
-    const StepConst K = make_step_const(C, a.dt, a.perturb_ratio);
+    const StepConst &K = a.K;
     Cell cache;
     cache.off = -1;
     State s;
