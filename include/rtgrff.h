@@ -173,9 +173,14 @@ int rtgrff_get_mw_slice(rtgrff_ctx *ctx, const int32_t *Lparms_M, const double *
  * per-pixel loop of script/resample_with_ray_tracing.py:467-530 (valid filter, Parms packing with
  * theta=90, flag 1+4, s_max 30; GET_MW; SFU -> T_b; V/I; nan_to_num) without materialising Parms.
  *  tb, vi: host float64 (n_rays, n_freq) (= emission_cube / emission_polVI_cube flattened over pixels).
+ *  s_input_on: the reference's --s-input-on (Parms[14] = S * area, :501).  The reference leaves the
+ *  meaning of that slot to a private GRFF build; this library defines it: a voxel's source term is
+ *  multiplied by Parms[14] / Rparms[0] = S (its own pencil cross-section instead of the pixel area),
+ *  absorption unchanged.  PyGET_MW and rtgrff_get_mw_slice honour Parms[14] > 0 the same way.
  */
 int rtgrff_emission_traced(rtgrff_ctx *ctx, double pixel_area_cm2, double freq0_hz, int n_freq,
-                           double freq_log_step, int em_flag, int s_max, double *tb, double *vi);
+                           double freq_log_step, int em_flag, int s_max, int s_input_on, double *tb,
+                           double *vi);
 
 /* Per-frequency settings of the fused map renderer. */
 typedef struct {
@@ -199,6 +204,10 @@ typedef struct {
  *  and outputs keep the caller's ray numbering.  Walking an image in small 2-D tiles instead of rows
  *  puts 32 neighbouring pixels into a warp and cuts the distinct cube cells it gathers from.
  *  use_bvec: 0 -> theta=90 deg (reference behaviour); 1 -> theta from B.t along the ray (needs bx,by,bz).
+ *  s_mode: which cross-section ratio a record carries (RTGRFF_S_PER_STEP as the reference's CPU path,
+ *  RTGRFF_S_CUMULATIVE as its CUDA path — then the pencil is traced at every step); it decides the
+ *  validity of a sample (S finite and > 0) and, with s_input_on (see rtgrff_emission_traced), the
+ *  factor on the voxel's source term.
  *  tb, vi: float64 (n_freq, n_rays); host, or device pointers when out_on_device != 0.
  *  stats (optional, host int64[4]): {nominal ray-steps, active ray-steps (the ray still moved),
  *  steps on which the two cross-section rays were traced, valid samples handed to the transfer}.
@@ -207,7 +216,27 @@ int rtgrff_render_map(rtgrff_ctx *ctx, int64_t n_rays, const double *x_start, co
                       const double *z_start, const double *kvec, const int32_t *ray_order, int n_freq,
                       const rtgrff_freq_params *freqs, int trace_cs, double perturb_ratio,
                       double pixel_area_cm2, double r_sun_cm, int em_flag, int s_max, int use_bvec,
-                      int voxel_order, double *tb, double *vi, int out_on_device, int64_t *stats);
+                      int voxel_order, int s_mode, int s_input_on, double *tb, double *vi,
+                      int out_on_device, int64_t *stats);
+
+/*
+ * Gaussian beam on the image plane: scipy.ndimage.gaussian_filter(map, sigma) as the workflow
+ * applies it to its T_b maps (script/resample_with_ray_tracing.py:618-624; baseline beam of
+ * script/pub/compare_on_off_scaling_factor.py:51-69): separable, kernel radius
+ * int(truncate*sigma+0.5) (scipy's truncate = 4.0), 'reflect' boundary, float64; NaN pixels spread
+ * as they do in scipy.  img, out: host float64 (n_planes, ny, nx); planes are filtered independently.
+ */
+int rtgrff_gaussian_beam(rtgrff_ctx *ctx, const double *img, int ny, int nx, int n_planes,
+                         double sigma_pix, double truncate, double *out);
+
+/*
+ * patch_nan_emission_map (raytracingGRFF/util.py:6-77): every non-finite pixel becomes the mean
+ * of the nearest finite pixels to its left, right, below and above (those that exist), visiting
+ * pixels in row-major order and patching in place, for up to max_passes sweeps (the reference's
+ * max_passes = 10).  img: host float64 (n_planes, ny, nx), patched in place; n_patched (optional).
+ */
+int rtgrff_patch_nan(rtgrff_ctx *ctx, double *img, int ny, int nx, int n_planes, int max_passes,
+                     int64_t *n_patched);
 
 #ifdef __cplusplus
 }

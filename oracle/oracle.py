@@ -307,3 +307,73 @@ def emission_from_los(Ne_LOS, Te_LOS, B_LOS, ds_LOS, pixel_area_cm2, freq0, Nfre
                 emission_cube[i, j, f] = inten * conv
                 emission_polVI_cube[i, j, f] = pol
     return emission_cube, emission_polVI_cube, frequencies_Hz
+
+
+# ---------------------------------------------------------------------------------------------
+# Image-plane post-processing
+# ---------------------------------------------------------------------------------------------
+def gaussian_filter(a, sigma, truncate=4.0):
+    """scipy.ndimage.gaussian_filter(a, sigma) for a 2-D float64 map, restated in numpy: the call the
+    workflow makes at script/resample_with_ray_tracing.py:618-624 and
+    script/pub/compare_on_off_scaling_factor.py:51-69.  Separable; per axis (0 first) a symmetric
+    correlation with weights exp(-x^2 / (2 sigma^2)) / sum over x = -r..r, r = int(truncate*sigma+0.5),
+    'reflect' boundary (d c b a | a b c d | d c b a).  Summation order as scipy's symmetric
+    correlate1d: centre tap, then the tap pairs from the farthest inwards."""
+    out = np.array(a, dtype=np.float64, copy=True)
+    r = int(truncate * float(sigma) + 0.5)
+    if sigma > 0:
+        x = np.arange(-r, r + 1)
+        w = np.exp(-0.5 / (sigma * sigma) * x ** 2)
+    else:
+        w = np.ones(1)
+    w = w / w.sum()
+    for axis in (0, 1):
+        n = out.shape[axis]
+        src = np.moveaxis(out, axis, 0)
+        idx = np.arange(-r, n + r)
+        period = 2 * n
+        idx = np.mod(idx, period)
+        idx = np.where(idx < n, idx, period - 1 - idx)
+        ext = src[idx]                                   # reflected line of length n + 2 r
+        acc = ext[r:r + n] * w[r]
+        for d in range(r, 0, -1):
+            acc = acc + (ext[r - d:r - d + n] + ext[r + d:r + d + n]) * w[r - d]
+        out = np.moveaxis(acc, 0, axis)
+    return np.ascontiguousarray(out)
+
+
+def _patch_plane(a, max_passes):
+    ny, nx = a.shape
+    for _ in range(max_passes):
+        bad = ~np.isfinite(a)                            # state at the start of the sweep (util.py:48)
+        if not bad.any():
+            return
+        fixed = 0
+        for i, j in zip(*np.nonzero(bad)):               # row-major order, patched in place (util.py:52-74)
+            vals = []
+            for line, pos, step in ((a[i, :], j, -1), (a[i, :], j, 1), (a[:, j], i, -1), (a[:, j], i, 1)):
+                q = pos + step                           # left, right, down, up: nearest finite pixel now
+                while 0 <= q < line.size:
+                    if np.isfinite(line[q]):
+                        vals.append(line[q])
+                        break
+                    q += step
+            if vals:
+                a[i, j] = np.mean(vals)
+                fixed += 1
+        if fixed == 0:
+            return
+
+
+def patch_nan_emission_map(emission, max_passes=10):
+    """raytracingGRFF/util.py:6-77 restated: non-finite pixels of a (ny,nx) map or of each [:, :, k]
+    slice of a (ny,nx,nf) cube become the mean of the nearest finite pixels left/right/below/above."""
+    out = np.array(emission, dtype=np.float64, copy=True)
+    if out.ndim == 2:
+        _patch_plane(out, max_passes)
+    elif out.ndim == 3:
+        for k in range(out.shape[2]):
+            _patch_plane(out[:, :, k], max_passes)
+    else:
+        raise ValueError("emission must be 2D or 3D")
+    return out

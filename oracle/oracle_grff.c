@@ -46,6 +46,13 @@
  *              between voxels (quasi-transverse layer): weak coupling swaps L,R; strong
  *              leaves them; exact mixes with Q=exp(-d),
  *              d = e^5/(32 pi^2 m^4 c^4) n_e B^3/(nu^4 |dtheta/dz|);
+ *   S input (Parms[14] > 0, the reference's --s-input-on, script/resample_with_ray_tracing.py:501):
+ *              the slot holds the voxel's source area S_k * area [cm^2], the cross-section of the
+ *              ray pencil there.  The reference hands it to a private GRFF build whose use of it is
+ *              not published; DEFINED HERE as: the voxel's emission into the pixel's flux scales
+ *              with its own area, i.e. its source term is multiplied by Parms[14] / Rparms[0]
+ *              (absorption unchanged; a gyroresonance layer between two voxels takes the factor
+ *              interpolated like its other parameters).  Parms[14] <= 0 (the default packing) leaves the factor 1;
  *   output:    RL[0]=nu/1e9, RL[1,2]=L,R weak, RL[3,4]=strong, RL[5,6]=exact, in sfu for
  *              source area Rparms[0] seen from 1 au.
  */
@@ -63,6 +70,7 @@
 
 typedef struct {
     double dz, T, ne, B, th, cth, sth;
+    double scale;                 /* source-term factor: Parms[14] / area when Parms[14] > 0, else 1 */
     int gr_on, ff_on, smax;
 } voxel_t;
 
@@ -143,7 +151,7 @@ static void qt_layer(double *I6, double nu, const voxel_t *p, const voxel_t *k)
     I6[5] = Q * Re + (1.0 - Q) * Le;
 }
 
-static void gr_layer(double *I6, double nu, int s, double ne, double T, double th, double LB)
+static void gr_layer(double *I6, double nu, int s, double ne, double T, double th, double LB, double scale)
 {
     const double cth = cos(th), sth = sin(th);
     const double Bres = nu * 2.0 * M_PI * M_EL * C_L / (s * Q_EL);
@@ -159,7 +167,7 @@ static void gr_layer(double *I6, double nu, int s, double ne, double T, double t
         const double pol = Ts * cth + Ls * sth + 1.0;
         double tau = M_PI * Q_EL * Q_EL * ne * LB / (M_EL * C_L * nu) * exp(lg) * pol * pol / (1.0 + Ts * Ts);
         if (!(tau > 0.0) || !isfinite(tau)) tau = 0.0;
-        apply_mode(I6, to_R, 1, tau, m.src);
+        apply_mode(I6, to_R, 1, tau, m.src * scale);
     }
 }
 
@@ -182,7 +190,7 @@ static void between(double *I6, double nu, const voxel_t *p, const voxel_t *k)
             const double ne = p->ne + t * (k->ne - p->ne), T = p->T + t * (k->T - p->T);
             const double th = p->th + t * (k->th - p->th);
             const double LB = Bres * dzm / fabs(k->B - p->B);
-            gr_layer(I6, nu, s, ne, T, th, LB);
+            gr_layer(I6, nu, s, ne, T, th, LB, p->scale + t * (k->scale - p->scale));
         }
     }
     if (!qt_done) qt_layer(I6, nu, p, k);
@@ -214,6 +222,7 @@ int oracle_get_mw(const int32_t *Lparms, const double *Rparms, const double *Par
             const int flag = (int)P[6];
             vx.gr_on = !(flag & 1); vx.ff_on = !(flag & 2);
             vx.smax = (int)P[7];
+            vx.scale = (P[14] > 0.0) ? P[14] / area : 1.0;
             if (!(vx.dz > 0.0) || !(vx.T > 0.0) || !(vx.ne > 0.0) || !(vx.B >= 0.0) ||
                 !isfinite(vx.dz) || !isfinite(vx.T) || !isfinite(vx.ne) || !isfinite(vx.B) || !isfinite(vx.th)) {
                 have_prev = 0;                               /* empty / invalid voxel: transparent, */
@@ -226,7 +235,7 @@ int oracle_get_mw(const int32_t *Lparms, const double *Rparms, const double *Par
                 mode_t m;
                 mode_eval(nu, vx.ne, vx.B, vx.T, vx.cth, vx.sth, sg, vx.ff_on, &m, 0, 0);
                 const int to_R = (sg < 0) ? x_to_R : !x_to_R;
-                apply_mode(I6, to_R, m.prop, m.kap * vx.dz, m.src);
+                apply_mode(I6, to_R, m.prop, m.kap * vx.dz, m.src * vx.scale);
             }
             prev = vx; have_prev = 1;
         }

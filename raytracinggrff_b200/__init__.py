@@ -2,12 +2,14 @@
 peijin94/raytracingGRFF behind the reference's own Python API.
 
 Exports mirror ``raytracingGRFF/__init__.py:3-15`` for the hot path (``C_R``, ``ray_trace``,
-``trace_ray``, ``sample_model_with_rays``); the MAS/psipy helpers and ``patch_nan_emission_map``
+``trace_ray``, ``sample_model_with_rays``, ``patch_nan_emission_map``); the MAS/psipy file readers
 are out of scope.  Nothing here imports ``oracle/``.
 """
 from .build_rays import ray_trace
 from .gpu_raytrace import C_R, sample_model_with_rays, trace_ray
 from .grff import get_mw_slice, initGET_MW
 from .session import RaySession
+from .util import patch_nan_emission_map
 
-__all__ = ["C_R", "RaySession", "get_mw_slice", "initGET_MW", "ray_trace", "sample_model_with_rays", "trace_ray"]
+__all__ = ["C_R", "RaySession", "get_mw_slice", "initGET_MW", "patch_nan_emission_map", "ray_trace",
+           "sample_model_with_rays", "trace_ray"]

@@ -35,7 +35,7 @@ EXPORTS = (
     "rtgrff_ctx_synchronize", "rtgrff_ctx_launch_count", "rtgrff_ctx_last_kernel_ms", "rtgrff_set_omega_cube", "rtgrff_set_field_cubes",
     "rtgrff_resample_spherical", "rtgrff_compose_cubes", "rtgrff_sample_spherical_los",
     "rtgrff_trace", "rtgrff_sample", "rtgrff_sample_traced", "PyGET_MW", "rtgrff_get_mw_slice",
-    "rtgrff_emission_traced", "rtgrff_render_map",
+    "rtgrff_emission_traced", "rtgrff_render_map", "rtgrff_gaussian_beam", "rtgrff_patch_nan",
 )
 
 
@@ -84,10 +84,12 @@ def load():
     lib.PyGET_MW.argtypes = [ip, dp, dp, dp, dp, dp, dp]
     lib.PyGET_MW.restype = c_int
     lib.rtgrff_get_mw_slice.argtypes = [c_void_p, ip, dp, dp, dp, dp, dp, dp, ip]
-    lib.rtgrff_emission_traced.argtypes = [c_void_p, c_double, c_double, c_int, c_double, c_int, c_int, dp, dp]
+    lib.rtgrff_emission_traced.argtypes = [c_void_p, c_double, c_double, c_int, c_double, c_int, c_int, c_int, dp, dp]
     lib.rtgrff_render_map.argtypes = [c_void_p, c_int64, dp, dp, dp, dp, ip, c_int, POINTER(FreqParams), c_int, c_double,
-                                      c_double, c_double, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
-                                      POINTER(c_int64)]
+                                      c_double, c_double, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                      c_int, POINTER(c_int64)]
+    lib.rtgrff_gaussian_beam.argtypes = [c_void_p, dp, c_int, c_int, c_int, c_double, c_double, dp]
+    lib.rtgrff_patch_nan.argtypes = [c_void_p, dp, c_int, c_int, c_int, c_int, POINTER(c_int64)]
     for name in EXPORTS:
         getattr(lib, name)          # AttributeError here = the .so is stale; rebuild it
     _lib = lib

@@ -44,6 +44,8 @@ struct MapArgs {
     double perturb_ratio, area;
     float r_sun_cm, fill_ne, fill_te, fill_b;
     int em_flag, s_max, use_bvec, order, cs_every_step;
+    int s_mode;                          // RTGRFF_S_PER_STEP / RTGRFF_S_CUMULATIVE: which S a record carries
+    int s_input;                         // the record's S scales the voxel's source term (--s-input-on)
     double *tb, *vi;                     // [freq][ray]
     unsigned long long *active_steps;    // [0] active central steps, [1] steps with the pencil traced, [2] valid samples
 };
@@ -146,7 +148,8 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_MINB) render_map_kernel(const Map
         }
     }
     bool alive = has_ray;
-    double s_step = CS ? 0.0 : 1.0;
+    double s_step = CS ? 0.0 : 1.0, s_cum = 1.0;
+    const bool cumulative = CS && a.s_mode == RTGRFF_S_CUMULATIVE;
     unsigned long long moved_steps = 0;
     unsigned int pencil_steps = 0, n_samples = 0;
     int64_t next_rec = 0;
@@ -159,8 +162,9 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_MINB) render_map_kernel(const Map
 
     for (int64_t i = 0; i < fp.n_steps; ++i) {
         if (alive) {
-            const bool want_s = CS && (i == next_rec || a.cs_every_step);
+            const bool want_s = CS && (i == next_rec || a.cs_every_step || cumulative);
             alive = advance_ray<CS, MODE>(C, K, cache, s, fp.dt, a.perturb_ratio, want_s, s_step);
+            if (cumulative) s_cum *= s_step;     // gpu_raytrace.py:398-408
             moved_steps += alive ? 1ull : 0ull;
             pencil_steps += (want_s && alive) ? 1u : 0u;
         }
@@ -168,7 +172,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_MINB) render_map_kernel(const Map
             next_rec += fp.stride;
             if (!tail_done) {
                 // --- sampler (float32, gpu_raytrace.py:642-650) ---
-                const float x = (float)s.rx, y = (float)s.ry, z = (float)s.rz, sv = (float)s_step;
+                const float x = (float)s.rx, y = (float)s.ry, z = (float)s.rz, sv = (float)(cumulative ? s_cum : s_step);
                 if (sample_valid(x, y, z, sv)) {
                     ++n_samples;
                     float3 bv = make_float3(0.f, 0.f, 0.f);
@@ -192,7 +196,10 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_MINB) render_map_kernel(const Map
                                 sth = sqrt(fmax(0.0, 1.0 - cth * cth));
                             }
                         }
-                        tr.push(fq, make_voxel_cs((double)ds, (double)f.te, (double)f.ne, bmag, cth, sth, a.em_flag, a.s_max));
+                        Voxel vx = make_voxel_cs((double)ds, (double)f.te, (double)f.ne, bmag, cth, sth, a.em_flag, a.s_max);
+                        // Parms[14] = S * area (script/resample_with_ray_tracing.py:501): source factor S
+                        if (a.s_input) vx.scale = (double)sv;
+                        tr.push(fq, vx);
                     }
                     px = x; py = y; pz = z;
                     first = false;

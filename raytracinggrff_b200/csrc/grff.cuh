@@ -33,6 +33,7 @@ constexpr double kSfu = 1e-19;
 
 struct Voxel {
     double dz, T, ne, B, cth, sth;   // theta enters through its cosine and sine only
+    double scale;                    // source-term factor of the S input (Parms[14] / area), 1 by default
     int smax;
     bool gr_on, ff_on, ok;
 };
@@ -62,6 +63,7 @@ __device__ __forceinline__ Voxel make_voxel_cs(double dz, double T, double ne, d
     Voxel v;
     v.dz = dz; v.T = T; v.ne = ne; v.B = B;
     v.cth = cth; v.sth = sth;
+    v.scale = 1.0;
     v.smax = smax;
     v.gr_on = !(flag & 1);
     v.ff_on = !(flag & 2);
@@ -178,7 +180,7 @@ __device__ __forceinline__ DiagOp voxel_op(const FreqC &f, const Voxel &v)
             pref = kKff * v.ne * v.ne * kZeta * lnL * f.inv_nu2 / (v.T * sqrt(v.T));
         }
     }
-    const double srcb = f.nu2 * kKbC2 * v.T;
+    const double srcb = f.nu2 * kKbC2 * v.T * v.scale;
     double aX = 0.0, bX = 0.0, aO = 0.0, bO = 0.0;
     if (u > 0.0) {
         const double s2 = v.sth * v.sth, c2 = v.cth * v.cth;
@@ -223,7 +225,7 @@ __device__ __forceinline__ DiagOp voxel_op(const FreqC &f, const Voxel &v)
 
 // One gyroresonance layer nu = s nu_B at interpolated plasma parameters.  Rare and heavy (lgamma,
 // log, exp, sincos): kept out of line so the hot loops stay small.
-__device__ __noinline__ DiagOp gr_layer_op(double nu, int s, double ne, double T, double th, double LB)
+__device__ __noinline__ DiagOp gr_layer_op(double nu, int s, double ne, double T, double th, double LB, double scale)
 {
     double sth, cth;
     sincos(th, &sth, &cth);
@@ -242,7 +244,7 @@ __device__ __noinline__ DiagOp gr_layer_op(double nu, int s, double ne, double T
             tau = kGrPref * ne * LB / nu * exp(lg) * pol * pol / (1.0 + Ts * Ts);
             if (!(tau > 0.0) || !isfinite(tau)) tau = 0.0;
         }
-        slab_ab(m.prop, tau, m.src, a[q], b[q]);
+        slab_ab(m.prop, tau, m.src * scale, a[q], b[q]);
     }
     return (cth >= 0.0) ? DiagOp{a[1], a[0], b[1], b[0]} : DiagOp{a[0], a[1], b[0], b[1]};
 }
@@ -289,7 +291,8 @@ __device__ __forceinline__ Between between_voxels(const FreqC &f, const Voxel &p
             if (!((p.B - Bres) * (k.B - Bres) < 0.0)) continue;
             const double t = (Bres - p.B) / (k.B - p.B);
             const DiagOp g = gr_layer_op(nu, s, p.ne + t * (k.ne - p.ne), p.T + t * (k.T - p.T),
-                                         th_p + t * (th_k - th_p), Bres * dzm / fabs(k.B - p.B));
+                                         th_p + t * (th_k - th_p), Bres * dzm / fabs(k.B - p.B),
+                                         p.scale + t * (k.scale - p.scale));
             if (t >= tqt) o.after = diag_then(o.after, g);
             else o.before = diag_then(o.before, g);
         }
@@ -342,9 +345,13 @@ struct SliceArgs {
     int npix, nz, nf;
 };
 
-__device__ __forceinline__ Voxel load_voxel(const double *P)
+// Parms[14] > 0 is the S input (script/resample_with_ray_tracing.py:501): the voxel's own source area
+// S_k * area; its source term scales by Parms[14] / area (definition in oracle/oracle_grff.c).
+__device__ __forceinline__ Voxel load_voxel(const double *P, double area)
 {
-    return make_voxel(P[0], P[1], P[2], P[3], P[4], (int)P[6], (int)P[7]);
+    Voxel v = make_voxel(P[0], P[1], P[2], P[3], P[4], (int)P[6], (int)P[7]);
+    if (P[14] > 0.0) v.scale = P[14] / area;
+    return v;
 }
 
 __device__ __forceinline__ DiagOp shfl_down_op(const DiagOp &d, int off)
@@ -372,10 +379,10 @@ __global__ void __launch_bounds__(128) grff_slice_kernel(const SliceArgs a)
         bt.qt = false;
         bool has_bt = false;
         if (k < a.nz) {
-            const Voxel v = load_voxel(P + (size_t)k * 15);
+            const Voxel v = load_voxel(P + (size_t)k * 15, R[0]);
             if (v.ok) {
                 if (k > 0) {
-                    const Voxel pv = load_voxel(P + (size_t)(k - 1) * 15);
+                    const Voxel pv = load_voxel(P + (size_t)(k - 1) * 15, R[0]);
                     if (pv.ok && pv.B > 0.0 && v.B > 0.0) { bt = between_voxels(fq, pv, v); has_bt = true; }
                 }
                 op = voxel_op<false>(fq, v);
@@ -459,6 +466,8 @@ __device__ __forceinline__ void tb_vi(double IL, double IR, double nu, double ar
 
 struct EmissionArgs {
     const float *ne, *te, *b, *ds;   // [rec][ray]
+    const float *s;                  // [rec][ray] cross-section ratio: the S input when s_input != 0
+    int s_input;
     const uint8_t *valid;
     int64_t n_rec, n_rays;
     double area, freq0, log_step;
@@ -482,7 +491,10 @@ __global__ void __launch_bounds__(128) emission_rays_kernel(const EmissionArgs a
         if (!a.valid[o]) continue;
         const float ne = a.ne[o], te = a.te[o], b = a.b[o];
         if (!(isfinite(ne) && isfinite(te) && isfinite(b))) continue;
-        tr.push(fq, make_voxel((double)a.ds[o], (double)te, (double)ne, (double)b, 90.0, a.em_flag, a.s_max));
+        Voxel v = make_voxel((double)a.ds[o], (double)te, (double)ne, (double)b, 90.0, a.em_flag, a.s_max);
+        // Parms[14] = S * area (script/resample_with_ray_tracing.py:501) -> source factor S where S > 0
+        if (a.s_input && a.s[o] > 0.0f) v.scale = (double)a.s[o];
+        tr.push(fq, v);
     }
     double tb, vi;
     tb_vi(tr.st.L[0], tr.st.R[0], nu, a.area, tb, vi);

@@ -10,6 +10,7 @@
 #include "cube_builder.cuh"
 #include "fused_map.cuh"
 #include "grff.cuh"
+#include "image_ops.cuh"
 #include "los_sampler.cuh"
 #include "ray_integrator.cuh"
 #include "trace_kernel.cuh"
@@ -605,7 +606,7 @@ int PyGET_MW(const int32_t *Lparms, const double *Rparms, const double *Parms, c
 }
 
 int rtgrff_emission_traced(rtgrff_ctx *c, double pixel_area_cm2, double freq0_hz, int n_freq, double freq_log_step,
-                           int em_flag, int s_max, double *tb, double *vi)
+                           int em_flag, int s_max, int s_input_on, double *tb, double *vi)
 {
     RT_TRY(use(c));
     if (c->smp_n <= 0 || c->smp_rays <= 0) return fail(RTGRFF_EINVAL, "no samples on the device (call rtgrff_sample_traced)");
@@ -616,6 +617,7 @@ int rtgrff_emission_traced(rtgrff_ctx *c, double pixel_area_cm2, double freq0_hz
     EmissionArgs a;
     a.ne = c->smp_ne.as<float>(); a.te = c->smp_te.as<float>(); a.b = c->smp_b.as<float>(); a.ds = c->smp_ds.as<float>();
     a.valid = c->smp_valid.as<uint8_t>();
+    a.s = c->smp_s.as<float>(); a.s_input = s_input_on ? 1 : 0;
     a.n_rec = c->smp_n; a.n_rays = c->smp_rays;
     a.area = pixel_area_cm2; a.freq0 = freq0_hz; a.log_step = freq_log_step;
     a.n_freq = n_freq; a.em_flag = em_flag; a.s_max = s_max;
@@ -635,7 +637,8 @@ int rtgrff_render_map(rtgrff_ctx *c, int64_t n_rays, const double *x_start, cons
                       const double *z_start, const double *kvec, const int32_t *ray_order, int n_freq,
                       const rtgrff_freq_params *freqs,
                       int trace_cs, double perturb_ratio, double pixel_area_cm2, double r_sun_cm, int em_flag, int s_max,
-                      int use_bvec, int voxel_order, double *tb, double *vi, int out_on_device, int64_t *stats)
+                      int use_bvec, int voxel_order, int s_mode, int s_input_on, double *tb, double *vi, int out_on_device,
+                      int64_t *stats)
 {
     RT_TRY(use(c));
     if (!c->has_wcube) return fail(RTGRFF_ENOCUBE, "rtgrff_set_omega_cube has not been called");
@@ -643,6 +646,8 @@ int rtgrff_render_map(rtgrff_ctx *c, int64_t n_rays, const double *x_start, cons
     if (use_bvec && !c->has_bvec) return fail(RTGRFF_ENOCUBE, "use_bvec needs bx,by,bz in rtgrff_set_field_cubes");
     if (n_rays < 0 || n_freq <= 0 || n_freq > 65535 || !freqs || !tb || !vi) return fail(RTGRFF_EINVAL, "bad arguments");
     if (voxel_order != RTGRFF_ORDER_RECORD && voxel_order != RTGRFF_ORDER_REVERSED) return fail(RTGRFF_EINVAL, "bad voxel_order");
+    if (s_mode != RTGRFF_S_PER_STEP && s_mode != RTGRFF_S_CUMULATIVE) return fail(RTGRFF_EINVAL, "bad s_mode");
+    if (s_input_on && !trace_cs) return fail(RTGRFF_EINVAL, "s_input_on needs the cross-sections traced (trace_cs)");
     if (n_rays > 0 && (!x_start || !y_start || !z_start)) return fail(RTGRFF_EINVAL, "null start arrays");
     if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
     if (n_rays == 0) return RTGRFF_OK;
@@ -691,6 +696,7 @@ int rtgrff_render_map(rtgrff_ctx *c, int64_t n_rays, const double *x_start, cons
     a.r_sun_cm = (float)r_sun_cm; a.fill_ne = 0.0f; a.fill_te = 1e4f; a.fill_b = 0.0f;
     a.em_flag = em_flag; a.s_max = s_max; a.use_bvec = use_bvec; a.order = voxel_order;
     a.cs_every_step = cs_every_step();
+    a.s_mode = s_mode; a.s_input = s_input_on ? 1 : 0;
     a.tb = dtb; a.vi = dvi;
     a.active_steps = c->counters.as<unsigned long long>();
     const dim3 block(RT_BLOCK);
@@ -736,6 +742,84 @@ int rtgrff_render_map(rtgrff_ctx *c, int64_t n_rays, const double *x_start, cons
     RT_TRY(d2h(c, act, c->counters.p, sizeof(act)));
     RT_CUDA(cudaStreamSynchronize(c->stream));
     if (stats) { stats[0] = nominal; stats[1] = (int64_t)act[0]; stats[2] = (int64_t)act[1]; stats[3] = (int64_t)act[2]; }
+    return RTGRFF_OK;
+}
+
+int rtgrff_gaussian_beam(rtgrff_ctx *c, const double *img, int ny, int nx, int n_planes, double sigma_pix,
+                         double truncate, double *out)
+{
+    RT_TRY(use(c));
+    if (!img || !out || ny < 1 || nx < 1 || n_planes < 1) return fail(RTGRFF_EINVAL, "bad arguments");
+    if (!(sigma_pix >= 0.0) || !isfinite(sigma_pix) || !(truncate > 0.0)) return fail(RTGRFF_EINVAL, "bad sigma/truncate");
+    const size_t n = (size_t)n_planes * ny * nx, nb = n * sizeof(double);
+    // scipy.ndimage._gaussian_kernel1d: radius = int(truncate*sigma + 0.5), exp(-x^2/(2 sigma^2)) / sum
+    const int radius = (int)(truncate * sigma_pix + 0.5);
+    std::vector<double> w(radius + 1);
+    double sum = 0.0;
+    for (int d = -radius; d <= radius; ++d) sum += sigma_pix > 0.0 ? exp(-0.5 / (sigma_pix * sigma_pix) * (double)d * (double)d) : (d == 0 ? 1.0 : 0.0);
+    for (int d = 0; d <= radius; ++d)
+        w[d] = (sigma_pix > 0.0 ? exp(-0.5 / (sigma_pix * sigma_pix) * (double)d * (double)d) : (d == 0 ? 1.0 : 0.0)) / sum;
+    RT_TRY(h2d(c, c->in0, img, nb));
+    RT_TRY(h2d(c, c->in1, w.data(), w.size() * sizeof(double)));
+    RT_TRY(c->out0.reserve(nb));
+    RT_TRY(c->out1.reserve(nb));
+    const unsigned int blocks = (unsigned int)std::min<int64_t>(blocks_for((int64_t)n, 256), (int64_t)c->sm_count * 32);
+    RT_CUDA(cudaEventRecord(c->ev0, c->stream));
+    // gaussian_filter runs the 1-D filter axis by axis: rows direction (axis 0) first, then axis 1
+    gaussian_pass_kernel<<<blocks, 256, 0, c->stream>>>(c->in0.as<double>(), c->out0.as<double>(), c->in1.as<double>(),
+                                                        radius, ny, nx, n_planes, 0);
+    RT_TRY(launched(c, "gaussian_pass_kernel"));
+    gaussian_pass_kernel<<<blocks, 256, 0, c->stream>>>(c->out0.as<double>(), c->out1.as<double>(), c->in1.as<double>(),
+                                                        radius, ny, nx, n_planes, 1);
+    RT_TRY(launched(c, "gaussian_pass_kernel"));
+    RT_CUDA(cudaEventRecord(c->ev1, c->stream));
+    c->ev_valid = true;
+    RT_TRY(d2h(c, out, c->out1.p, nb));
+    RT_CUDA(cudaStreamSynchronize(c->stream));
+    return RTGRFF_OK;
+}
+
+int rtgrff_patch_nan(rtgrff_ctx *c, double *img, int ny, int nx, int n_planes, int max_passes, int64_t *n_patched)
+{
+    RT_TRY(use(c));
+    if (!img || ny < 1 || nx < 1 || n_planes < 1 || max_passes < 0) return fail(RTGRFF_EINVAL, "bad arguments");
+    if (n_patched) *n_patched = 0;
+    const size_t n = (size_t)n_planes * ny * nx, nb = n * sizeof(double);
+    RT_TRY(h2d(c, c->in0, img, nb));
+    RT_TRY(c->out0.reserve(nb));
+    RT_TRY(c->out1.reserve(nb));
+    RT_TRY(c->out2.reserve(n));
+    RT_TRY(c->counters.reserve(64 + (size_t)n_planes * sizeof(int)));
+    int *d_any = c->counters.as<int>();
+    int *d_fixed = reinterpret_cast<int *>(c->counters.as<char>() + 64);
+    const unsigned int blocks = (unsigned int)std::min<int64_t>(blocks_for((int64_t)n, 256), (int64_t)c->sm_count * 32);
+    std::vector<int> fixed(n_planes);
+    int64_t total = 0;
+    // _patch_nan_2d (util.py:45-76): up to max_passes sweeps; stop when nothing is left or nothing could be fixed
+    for (int pass = 0; pass < max_passes; ++pass) {
+        RT_CUDA(cudaMemsetAsync(c->counters.p, 0, 64 + (size_t)n_planes * sizeof(int), c->stream));
+        mark_nonfinite_kernel<<<blocks, 256, 0, c->stream>>>(c->in0.as<double>(), c->out2.as<unsigned char>(), (int64_t)n, d_any);
+        RT_TRY(launched(c, "mark_nonfinite_kernel"));
+        int any = 0;
+        RT_TRY(d2h(c, &any, d_any, sizeof(int)));
+        RT_CUDA(cudaStreamSynchronize(c->stream));
+        if (!any) break;
+        next_finite_kernel<<<blocks_for((int64_t)n_planes * (ny + nx), 128), 128, 0, c->stream>>>(
+            c->in0.as<double>(), c->out0.as<double>(), c->out1.as<double>(), ny, nx, n_planes);
+        RT_TRY(launched(c, "next_finite_kernel"));
+        patch_nan_pass_kernel<<<n_planes, 1024, 0, c->stream>>>(c->in0.as<double>(), c->out2.as<unsigned char>(),
+                                                                c->out0.as<double>(), c->out1.as<double>(), ny, nx, d_fixed);
+        RT_TRY(launched(c, "patch_nan_pass_kernel"));
+        RT_TRY(d2h(c, fixed.data(), d_fixed, (size_t)n_planes * sizeof(int)));
+        RT_CUDA(cudaStreamSynchronize(c->stream));
+        int64_t f = 0;
+        for (int v : fixed) f += v;
+        total += f;
+        if (f == 0) break;
+    }
+    RT_TRY(d2h(c, img, c->in0.p, nb));
+    RT_CUDA(cudaStreamSynchronize(c->stream));
+    if (n_patched) *n_patched = total;
     return RTGRFF_OK;
 }
 

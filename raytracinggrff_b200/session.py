@@ -12,6 +12,18 @@ from . import _lib
 from ._lib import FreqParams, check, f32, f64, ptr
 
 
+def _s_mode(v):
+    """'per_step' / 'cumulative' (or the RTGRFF_S_* integers) -> RTGRFF_S_*."""
+    if isinstance(v, str):
+        try:
+            return {"per_step": _lib.S_PER_STEP, "cumulative": _lib.S_CUMULATIVE}[v.lower()]
+        except KeyError:
+            raise ValueError(f"Unsupported s_mode '{v}'. Use 'per_step' or 'cumulative'.") from None
+    if int(v) not in (_lib.S_PER_STEP, _lib.S_CUMULATIVE):
+        raise ValueError(f"Unsupported s_mode {v!r}")
+    return int(v)
+
+
 class RaySession:
     def __init__(self, device=0, stream=None, context=None):
         self.ctx = context if context is not None else _lib.Context(device, stream)
@@ -88,7 +100,7 @@ class RaySession:
         active = c_int64(0)
         check(self._lib.rtgrff_trace(self.ctx.handle, n_rays, ptr(xs, c_double), ptr(ys, c_double), ptr(zs, c_double),
                                      ptr(kv, c_double), float(freq_hz), float(dt), n_steps, stride,
-                                     int(bool(trace_crosssections)), float(perturb_ratio), int(s_mode),
+                                     int(bool(trace_crosssections)), float(perturb_ratio), _s_mode(s_mode),
                                      ptr(r_record, c_double), ptr(s_record, c_double), ctypes.byref(active)))
         self.n_rec, self.n_rays, self.traced_cs = n_rec, n_rays, bool(trace_crosssections)
         return r_record, s_record, int(active.value)
@@ -154,27 +166,31 @@ class RaySession:
                                             None, None, None, ptr(RL_M, c_double), ptr(status, ctypes.c_int32)))
         return status
 
-    def emission_traced(self, pixel_area_cm2, freq0, n_freq=1, freq_log_step=0.0, em_flag=5, s_max=30):
+    def emission_traced(self, pixel_area_cm2, freq0, n_freq=1, freq_log_step=0.0, em_flag=5, s_max=30,
+                        s_input_on=False):
         """script/resample_with_ray_tracing.py:467-530 on the device samples; returns (tb, vi) each
         (n_rays, n_freq) float64."""
         tb = np.empty((self.n_rays, int(n_freq)), dtype=np.float64)
         vi = np.empty_like(tb)
         check(self._lib.rtgrff_emission_traced(self.ctx.handle, float(pixel_area_cm2), float(freq0), int(n_freq),
-                                               float(freq_log_step), int(em_flag), int(s_max), ptr(tb, c_double),
-                                               ptr(vi, c_double)))
+                                               float(freq_log_step), int(em_flag), int(s_max), int(bool(s_input_on)),
+                                               ptr(tb, c_double), ptr(vi, c_double)))
         return tb, vi
 
     # -- fused map -----------------------------------------------------------------------------
     def render_map(self, x_start, y_start, z_start, freq_params, kvec_in_norm=None, trace_crosssections=True,
                    perturb_ratio=2.0, pixel_area_cm2=1.0, r_sun_cm=6.957e10, em_flag=5, s_max=30, use_bvec=False,
-                   voxel_order=_lib.ORDER_RECORD, out_device_ptrs=None, image_shape=None, tile=(4, 8), ray_order=None):
+                   voxel_order=_lib.ORDER_RECORD, out_device_ptrs=None, image_shape=None, tile=(4, 8), ray_order=None,
+                   s_mode="per_step", s_input_on=False):
         """Fused trace+sample+transfer.  freq_params: sequence of dicts/tuples
         (freq_hz, dt, n_steps, record_stride).  Returns (tb, vi) each (n_freq, n_rays) float64 and
         stats {nominal_ray_steps, active_ray_steps}; with out_device_ptrs=(tb_ptr, vi_ptr) the
         results are written to those device buffers instead and (None, None, stats) is returned.
         image_shape=(n_rows, n_cols): the rays are a row-major image (ray p = i*n_cols + j); threads
         then walk it in `tile` = (width, height) pixel tiles, which keeps a warp's 32 rays in a compact
-        patch (-11 % on config 4); results keep the caller's ray numbering."""
+        patch (-11 % on config 4); results keep the caller's ray numbering.
+        s_mode 'per_step' | 'cumulative': the cross-section ratio a record carries (reference CPU / CUDA
+        path); s_input_on: that S multiplies the voxel's source term (``--s-input-on``, see include/rtgrff.h)."""
         xs, ys, zs = f64(x_start).ravel(), f64(y_start).ravel(), f64(z_start).ravel()
         n_rays = xs.shape[0]
         kv = None
@@ -211,6 +227,7 @@ class RaySession:
                                           ptr(zs, c_double), ptr(kv, c_double), ptr(order, ctypes.c_int32), nf, arr,
                                           int(bool(trace_crosssections)), float(perturb_ratio), float(pixel_area_cm2),
                                           float(r_sun_cm), int(em_flag), int(s_max), int(bool(use_bvec)),
-                                          int(voxel_order), ptb, pvi, on_dev, stats))
+                                          int(voxel_order), _s_mode(s_mode), int(bool(s_input_on)), ptb, pvi, on_dev,
+                                          stats))
         return tb, vi, {"nominal_ray_steps": int(stats[0]), "active_ray_steps": int(stats[1]),
                         "pencil_steps": int(stats[2]), "valid_samples": int(stats[3])}

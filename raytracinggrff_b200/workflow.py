@@ -84,7 +84,7 @@ def run_ray_tracing_emission(model, N_pix=64, X_fov=1.44, freq_hz=75e6, z_observ
                              record_stride=10, n_workers=1, s_input_on=False, out_path=None, grff_lib=None, Nfreq=1,
                              freq0=None, freq_log_step=0.0, save_plots=False, verbose=True, device="cuda",
                              fallback_to_cpu=False, raytrace_device="cuda", grff_backend="get_mw",
-                             perturb_ratio=2, session=None, return_samples=False):
+                             perturb_ratio=2, session=None, return_samples=False, s_mode="per_step"):
     if freq0 is None:
         freq0 = freq_hz
     backend = grff_backend.lower()
@@ -92,9 +92,10 @@ def run_ray_tracing_emission(model, N_pix=64, X_fov=1.44, freq_hz=75e6, z_observ
         raise ValueError(f"Unsupported grff_backend '{grff_backend}'. Use 'get_mw', 'fastgrff', 'device' or 'fused'.")
     _check_device("device", device)
     _check_device("raytrace_device", raytrace_device)
-    if s_input_on:
-        raise NotImplementedError("s_input_on relies on a private GRFF build (Parms[14] = S*area is a reserved "
-                                  "slot upstream); its semantics are not defined by the reference")
+    # s_input_on (script/resample_with_ray_tracing.py:501): Parms[14] = S * area.  The reference leaves the
+    # meaning of that slot to a private GRFF build; here the voxel's source term is multiplied by
+    # Parms[14] / area = S (include/rtgrff.h).  s_mode picks the S of the reference's CPU path (per step,
+    # ~1) or of its CUDA path (cumulative since the start of the ray: the pencil's magnification).
     ses = session or RaySession(context=_lib.default_context(0))
     xg, yg, zg = model["x_grid"], model["y_grid"], model["z_grid"]
     ses.set_omega_cube(model["omega_pe"], xg, yg, zg)
@@ -118,16 +119,17 @@ def run_ray_tracing_emission(model, N_pix=64, X_fov=1.44, freq_hz=75e6, z_observ
                              "(or RaySession.render_map for a list of frequencies)")
         tb, vi, _ = ses.render_map(x_flat, y_flat, z_start, [(freq_hz, dt, n_steps, record_stride)],
                                    kvec_in_norm=kvec, trace_crosssections=True, perturb_ratio=perturb_ratio,
-                                   pixel_area_cm2=area, r_sun_cm=R_sun_cm, image_shape=(N_pix, N_pix))
+                                   pixel_area_cm2=area, r_sun_cm=R_sun_cm, image_shape=(N_pix, N_pix),
+                                   s_mode=s_mode, s_input_on=s_input_on)
         emission_cube[:, :, 0] = tb[0].reshape(N_pix, N_pix)
         emission_polVI_cube[:, :, 0] = vi[0].reshape(N_pix, N_pix)
     else:
         keep_host = backend in ("get_mw", "fastgrff") or return_samples
         ses.trace(freq_hz, x_flat, y_flat, z_start, kvec, dt, n_steps, record_stride, True, perturb_ratio,
-                  fetch=False)
+                  s_mode=s_mode, fetch=False)
         sampled = ses.sample_traced(ray_start, R_sun_cm, 0.0, 1e4, 0.0, fetch=keep_host)
         if backend == "device":
-            tb, vi = ses.emission_traced(area, freq0, Nf, freq_log_step)
+            tb, vi = ses.emission_traced(area, freq0, Nf, freq_log_step, s_input_on=s_input_on)
             emission_cube[:] = tb.reshape(N_pix, N_pix, Nf)
             emission_polVI_cube[:] = vi.reshape(N_pix, N_pix, Nf)
         elif backend == "fastgrff":
@@ -166,6 +168,8 @@ def run_ray_tracing_emission(model, N_pix=64, X_fov=1.44, freq_hz=75e6, z_observ
                 Parms[4] = 90.0
                 Parms[6] = 1 + 4
                 Parms[7] = 30
+                if s_input_on:
+                    Parms[14] = sampled["s"][:, p][valid] * area
                 L = Lparms.copy()
                 L[0] = n_valid
                 RL = np.zeros((7, Nf), dtype="double", order="F")

@@ -62,7 +62,7 @@ def main():
             t = timeit(lambda: ses.render_map(xs, ys, zs, fp, kvec_in_norm=kv, pixel_area_cm2=area), n=2)
             print(f"C4 fused f={f/1e6:.0f}MHz: {t*1e3:.1f} ms nominal {st['nominal_ray_steps']/t:.3e} active {st['active_ray_steps']/t:.3e} ray-steps/s")
     if which == "c4freq":
-        c = synthetic.corona_cube(256, 3.0, active_region=True)
+        c = synthetic.corona_cube(int(os.environ.get("RTGRFF_G", "256")), 3.0, active_region=True)
         ses.set_omega_cube(c["omega_pe"], c["x_grid"], c["y_grid"], c["z_grid"])
         ses.set_field_cubes(c["x_grid"], c["y_grid"], c["z_grid"], c["ne"], c["te"], c["b"], c["bx"], c["by"], c["bz"])
         xs, ys, zs, kv = synthetic.ray_launch_geometry(512, 1.44, 3.0)

@@ -76,3 +76,42 @@ def trace_case(name):
 
 
 TRACE_CASES = ("corona_cs", "oblique_nocs", "c3_subset")
+
+
+def image_case(name):
+    """Emission maps with failed pixels for the image-plane operations (T_b-like values)."""
+    rng = np.random.default_rng({"sparse": 11, "clusters": 12, "cube": 13, "rows": 14}[name])
+    if name == "sparse":
+        a = 1e6 * (1.0 + rng.random((37, 45)))
+        a[rng.random(a.shape) < 0.03] = np.nan
+        a[5, 7] = np.inf
+        return a
+    if name == "clusters":
+        # runs of NaN along rows and columns, a NaN block, NaN corners and a NaN border row
+        a = 5e5 + 1e5 * rng.standard_normal((40, 33))
+        a[10, 3:20] = np.nan
+        a[4:30, 25] = np.nan
+        a[20:26, 8:15] = np.nan
+        a[0, :] = np.nan
+        a[-1, -1] = np.nan
+        a[0, 0] = np.nan
+        return a
+    if name == "rows":
+        # whole rows and columns missing: some pixels have no finite pixel in one or two directions
+        a = 1e6 * rng.random((21, 19))
+        a[:, 4] = np.nan
+        a[7, :] = np.nan
+        a[:3, :3] = np.nan
+        return a
+    if name == "cube":
+        # (ny, nx, nf): one clean plane, one sparse, one with nothing finite at all
+        a = 1e6 * (1.0 + rng.random((24, 28, 3)))
+        m = rng.random((24, 28)) < 0.1
+        a[m, 1] = np.nan
+        a[:, :, 2] = np.nan
+        return a
+    raise KeyError(name)
+
+
+IMAGE_CASES = ("sparse", "clusters", "rows", "cube")
+BEAM_SIGMAS = (0.0, 0.7, 2.5, 11.0, 60.0)

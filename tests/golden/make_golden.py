@@ -83,6 +83,22 @@ def main():
     exec(code, ns)
     freqs = [20e6, 30e6, 75e6, 100e6, 150e6, 150.0001e6, 200e6, 279e6, 280e6, 400e6, 550e6, 700e6, 800e6, 1.2e9]
     json.dump({repr(f): ns["select_params"](f) for f in freqs}, open(out / "select_params.json", "w"), indent=1)
+    # image-plane operations: the reference's own patch_nan_emission_map (util.py is loaded by path: the
+    # package __init__ would import matplotlib/psipy users) and the scipy call the workflow makes
+    import importlib.util
+    from scipy.ndimage import gaussian_filter
+    spec = importlib.util.spec_from_file_location("ref_util", REF / "raytracingGRFF" / "util.py")
+    ref_util = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_util)
+    img = {}
+    for name in cases.IMAGE_CASES:
+        a = cases.image_case(name)
+        img[f"patch_{name}"] = ref_util.patch_nan_emission_map(a)
+    smooth = ref_util.patch_nan_emission_map(cases.image_case("sparse"))
+    for sg in cases.BEAM_SIGMAS:
+        img[f"beam_{sg}"] = gaussian_filter(smooth, sigma=sg)
+    img["beam_nan_2.5"] = gaussian_filter(cases.image_case("sparse"), sigma=2.5)
+    np.savez_compressed(out / "image_ops.npz", **img)
     print("golden vectors written to", out)
 
 

@@ -170,7 +170,34 @@ def check_gyroresonance_layer(get_mw):
     assert np.all(RL_s2[1:] == 0.0)
 
 
-ALL_CHECKS = [check_frequency_grid_and_codes, check_optically_thick_isothermal, check_optically_thin_free_free,
+def check_s_input_scales_the_source(get_mw):
+    """Parms[14] > 0 = the voxel's own source area S*area (--s-input-on, script/...:501).  Defined in
+    oracle/oracle_grff.c: the voxel's source term is multiplied by Parms[14]/Rparms[0], absorption
+    unchanged.  Optically thin: emission scales by S; optically thick uniform S: T_b -> S*T; a
+    foreground voxel with S = 1 in front of a thick S = 3 slab absorbs like any other."""
+    T, ne, nu = 1.0e6, 2.0e8, 3.0e9
+    thin = parms(8, 1e7, T, ne, 0.0)
+    base = run(get_mw, thin, nu)
+    for S in (0.5, 1.0, 2.5):
+        P = thin.copy(order="F")
+        P[14] = S * AREA
+        RL = run(get_mw, P, nu)
+        np.testing.assert_allclose(RL[5:], S * base[5:], rtol=2e-6)      # thin: tau ~ 1e-5, (1 - S tau/2 ...) ~ 1
+    # Parms[14] = 0 (the reference's default packing) and Parms[14] = area are the same map
+    P = thin.copy(order="F")
+    P[14] = AREA
+    np.testing.assert_allclose(run(get_mw, P, nu)[5:], base[5:], rtol=1e-14)
+    thick = parms(64, 1e9, T, 3e9, 0.0)
+    thick[14] = 3.0 * AREA
+    np.testing.assert_allclose(tb_of(run(get_mw, thick, 1.0e9))[0], 3.0 * T * (1 - 8.06163860e7 * 3e9 / 1e18), rtol=2e-3)
+    # per-voxel factors: S ramps along a thin LOS -> emission = sum S_k * e_k
+    P = thin.copy(order="F")
+    Sk = np.linspace(0.2, 1.8, 8)
+    P[14] = Sk * AREA
+    np.testing.assert_allclose(run(get_mw, P, nu)[5:], Sk.mean() * base[5:], rtol=1e-5)
+
+
+ALL_CHECKS = [check_s_input_scales_the_source, check_frequency_grid_and_codes, check_optically_thick_isothermal, check_optically_thin_free_free,
               check_polarisation_sign_and_magnitude, check_cutoff_blocks_background, check_mode_coupling_limits,
               check_gyroresonance_layer]
 

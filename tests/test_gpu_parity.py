@@ -324,6 +324,35 @@ def test_run_ray_tracing_emission_matches_oracle_chain(oracle, backend):
     _cmp_maps(res["emission_cube"], res["emission_polVI_cube"], tb_ref, vi_ref)
 
 
+@pytest.mark.parametrize("backend", ["get_mw", "fastgrff", "device", "fused"])
+@pytest.mark.parametrize("s_mode", ["per_step", "cumulative"])
+def test_s_input_on_matches_oracle_chain(oracle, backend, s_mode):
+    """--s-input-on (script/resample_with_ray_tracing.py:501: Parms[14] = S * area) through every
+    backend, with the S of the reference's CPU path (per step) and of its CUDA path (cumulative
+    product, gpu_raytrace.py:398-408), against oracle trace -> sampler -> GET_MW fed the same
+    Parms[14].  The cumulative S of the oracle is the running product of its per-step ratios."""
+    from raytracinggrff_b200.workflow import run_ray_tracing_emission
+    c = synthetic.corona_cube(48, 3.0)
+    N_pix, X_fov, z_obs, freq, dt, n_steps, stride = 8, 1.44, 3.0, 75e6, 6e-3, 3000, 6
+    xs, ys, zs, kv = synthetic.ray_launch_geometry(N_pix, X_fov, z_obs)
+    r1, cs1 = oracle.ray_trace(c["omega_pe"], c["x_grid"], c["y_grid"], c["z_grid"], freq, xs, ys, zs, kv, dt, n_steps,
+                               1, True, perturb_ratio=2)
+    s_all = np.array(cs1)
+    if s_mode == "cumulative":
+        s_all = np.cumprod(s_all, axis=0)
+    smp = oracle.sample_model_with_rays_cpu(c["x_grid"], c["y_grid"], c["z_grid"], c["ne"], c["te"], c["b"],
+                                            r1[::stride], s_all[::stride], np.column_stack([xs, ys, zs]), 6.957e10)
+    tb_ref, vi_ref, _ = oracle.emission_from_samples(smp, N_pix, X_fov, freq, s_input_on=True)
+    tb_off, _, _ = oracle.emission_from_samples(smp, N_pix, X_fov, freq, s_input_on=False)
+    res = run_ray_tracing_emission(c, N_pix=N_pix, X_fov=X_fov, freq_hz=freq, z_observer=z_obs, dt=dt, n_steps=n_steps,
+                                   record_stride=stride, grff_backend=backend, s_input_on=True, s_mode=s_mode,
+                                   verbose=False)
+    _cmp_maps(res["emission_cube"], res["emission_polVI_cube"], tb_ref, vi_ref)
+    # the S input changes the map (by the pencil's magnification in cumulative mode)
+    on = tb_ref != 0
+    assert np.abs(tb_ref[on] / tb_off[on] - 1).max() > (1e-3 if s_mode == "cumulative" else 1e-6)
+
+
 def test_render_map_multi_frequency_and_orders(oracle, session):
     """Fused map at three frequencies with per-frequency presets; record order (reference behaviour)
     and reversed order (far end first) against the oracle fed the same / reversed voxel lists;

@@ -124,3 +124,24 @@ def test_pack_parms_batch_matches_reference_loop(oracle):
     area = pixel_area_cm2(1.44, 64)
     np.testing.assert_array_equal(pack_parms_batch(smp, area), oracle.pack_parms_batch(smp, area))
     assert pack_parms_batch(smp, area).flags.f_contiguous
+
+
+def test_dlogS_ds_diagnostic():
+    """script/pub/cross_section_plots.ipynb cell 12, restated inline."""
+    from raytracinggrff_b200.util import dlogS_ds
+    rng = np.random.default_rng(2)
+    r = np.cumsum(rng.random((50, 4, 3)) * 0.01, axis=0)
+    S = np.cumprod(1 + 0.01 * rng.standard_normal((50, 4)), axis=0)
+    S[10, 1] = 0.001
+    S[20:, 3] = np.nan
+    got = dlogS_ds(r, S, distance_ray=0)
+    Sm = S.copy()
+    Sm[Sm < 0.01] = np.nan
+    d = np.diff(np.log(Sm), axis=0)
+    dist = np.concatenate([[0], np.cumsum(np.sqrt(np.sum(np.diff(r[:, 0, :], axis=0) ** 2, axis=1)))])
+    ref = d / np.tile(np.diff(dist), (d.shape[1], 1)).T
+    ref[np.isnan(ref)] = 0
+    ref[np.isinf(ref)] = 0
+    np.testing.assert_allclose(got, ref, rtol=1e-12)
+    own = dlogS_ds(r, S)
+    assert own.shape == (49, 4) and np.all(own[20:, 3] == 0) and own[9, 1] == 0 and own[10, 1] == 0
