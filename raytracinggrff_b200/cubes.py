@@ -89,3 +89,23 @@ def set_model_from_spherical(session, model, x_grid, y_grid, z_grid, phi0_offset
     for name, fill in (("rho", 0.0), (temp, None), ("br", 0.0), ("bt", 0.0), ("bp", 0.0)):
         _resample(ctx, SLOTS[name], model[name], x_grid, y_grid, z_grid, phi0_offset, fill, r_min, False)
     check(_lib.load().rtgrff_compose_cubes(ctx.handle, int(bool(want_bvec))))
+
+
+def save_spherical_model(path, model):
+    """Write a model (name -> SphericalVariable) to one .npz: the in-memory stand-in for a MAS directory
+    that the command lines accept (``--model-path``)."""
+    arrays = {}
+    for name, v in model.items():
+        arrays[f"{name}__data"] = np.asarray(v.data, dtype=np.float32)
+        arrays[f"{name}__phi"], arrays[f"{name}__lat"], arrays[f"{name}__r"] = f64(v.phi), f64(v.lat), f64(v.r)
+        arrays[f"{name}__scale"] = np.float64(v.scale)
+    np.savez_compressed(path, **arrays)
+
+
+def load_spherical_model(path):
+    """Inverse of save_spherical_model.  Raises FileNotFoundError like the reference does for a missing
+    model directory."""
+    with np.load(path) as z:
+        names = sorted({k.split("__")[0] for k in z.files})
+        return {n: SphericalVariable(z[f"{n}__data"], z[f"{n}__phi"], z[f"{n}__lat"], z[f"{n}__r"],
+                                     float(z[f"{n}__scale"])) for n in names}

@@ -84,7 +84,8 @@ def run_ray_tracing_emission(model, N_pix=64, X_fov=1.44, freq_hz=75e6, z_observ
                              record_stride=10, n_workers=1, s_input_on=False, out_path=None, grff_lib=None, Nfreq=1,
                              freq0=None, freq_log_step=0.0, save_plots=False, verbose=True, device="cuda",
                              fallback_to_cpu=False, raytrace_device="cuda", grff_backend="get_mw",
-                             perturb_ratio=2, session=None, return_samples=False, s_mode="per_step"):
+                             perturb_ratio=2, session=None, return_samples=False, s_mode="per_step",
+                             grid_n=128, grid_extent=3.0, phi0_offset=0.0, consider_beam=False, beam_fwhm=0.2):
     if freq0 is None:
         freq0 = freq_hz
     backend = grff_backend.lower()
@@ -97,9 +98,14 @@ def run_ray_tracing_emission(model, N_pix=64, X_fov=1.44, freq_hz=75e6, z_observ
     # Parms[14] / area = S (include/rtgrff.h).  s_mode picks the S of the reference's CPU path (per step,
     # ~1) or of its CUDA path (cumulative since the start of the ray: the pencil's magnification).
     ses = session or RaySession(context=_lib.default_context(0))
-    xg, yg, zg = model["x_grid"], model["y_grid"], model["z_grid"]
-    ses.set_omega_cube(model["omega_pe"], xg, yg, zg)
-    ses.set_field_cubes(xg, yg, zg, model["ne"], model["te"], model["b"])
+    if "omega_pe" in model:
+        xg, yg, zg = model["x_grid"], model["y_grid"], model["z_grid"]
+        ses.set_omega_cube(model["omega_pe"], xg, yg, zg)
+        ses.set_field_cubes(xg, yg, zg, model["ne"], model["te"], model["b"])
+    else:
+        # a spherical (phi, latitude, r) model: the cube resampling of :251-293 on the GPU
+        xg = yg = zg = np.linspace(-grid_extent, grid_extent, int(grid_n))
+        ses.set_model_from_spherical(model, xg, yg, zg, phi0_offset=phi0_offset)
 
     x_flat, y_flat, z_start, kvec = synthetic.ray_launch_geometry(N_pix, X_fov, z_observer)
     n_rays = len(x_flat)
@@ -187,8 +193,68 @@ def run_ray_tracing_emission(model, N_pix=64, X_fov=1.44, freq_hz=75e6, z_observ
         "x_coords": x_coords,
         "y_coords": y_coords,
     }
+    if consider_beam:
+        # --consider-beam (:618-624): the reference convolves the plotted map only; here the convolved
+        # map is returned (and saved) next to the raw cube
+        from .util import convolve_beam
+        beam = emission_cube[:, :, 0].copy()
+        beam[beam == 0] = np.nan
+        result["emission_map_beam"] = convolve_beam(beam, beam_fwhm, [-X_fov, X_fov], N_pix)
     if out_path is not None:
         np.savez_compressed(out_path, **result)
     if return_samples and sampled:
         result["sampled"] = sampled
     return result
+
+
+def main(argv=None):
+    """Command line of script/resample_with_ray_tracing.py:652-730 with the same flags.  ``--model-path``
+    is an .npz of spherical variables (raytracinggrff_b200.cubes.save_spherical_model) or 'synthetic'
+    (the analytic corona) instead of a MAS directory: reading MAS HDF files needs psipy (out of scope)."""
+    import argparse
+    parser = argparse.ArgumentParser(description="Ray-tracing emission map on the GPU (librtgrff_b200).")
+    parser.add_argument("--model-path", "-m", type=str, default="synthetic")
+    parser.add_argument("--N-pix", "-n", type=int, default=32)
+    parser.add_argument("--X-FOV", "-f", type=float, default=1.44)
+    parser.add_argument("--freq", type=float, default=75e6)
+    parser.add_argument("--grid-n", type=int, default=128)
+    parser.add_argument("--grid-extent", type=float, default=3.0)
+    parser.add_argument("--z-observer", type=float, default=3.0)
+    parser.add_argument("--dt", type=float, default=6e-3)
+    parser.add_argument("--n-steps", type=int, default=5000)
+    parser.add_argument("--record-stride", type=int, default=10)
+    parser.add_argument("--workers", "-w", type=int, default=1, help="accepted for compatibility; rays run on one GPU")
+    parser.add_argument("--out-path", "-o", type=str, default="ray_tracing_emission.npz")
+    parser.add_argument("--grff-lib", type=str, default=None, help="library exporting PyGET_MW (default: librtgrff_b200.so)")
+    parser.add_argument("--grff-backend", type=str, default="get_mw", choices=["get_mw", "fastgrff", "device", "fused"])
+    parser.add_argument("--s-input-on", action="store_true")
+    parser.add_argument("--s-mode", type=str, default="per_step", choices=["per_step", "cumulative"])
+    parser.add_argument("--device", type=str, default="cuda", choices=["cpu", "cuda"])
+    parser.add_argument("--raytrace-device", type=str, default="cuda", choices=["cpu", "cuda"])
+    parser.add_argument("--consider-beam", action="store_true")
+    parser.add_argument("--beam-fwhm", type=float, default=0.2)
+    parser.add_argument("--phi0-offset", type=float, default=0)
+    parser.add_argument("--no-fallback", action="store_true", help="accepted for compatibility; there is no CPU path to fall back to")
+    parser.add_argument("--no-plots", action="store_true", help="accepted for compatibility; no plots are made")
+    parser.add_argument("--quiet", "-q", action="store_true")
+    args = parser.parse_args(argv)
+    if args.model_path == "synthetic":
+        model = synthetic.spherical_corona()
+    else:
+        from .cubes import load_spherical_model
+        model = load_spherical_model(args.model_path)
+    res = run_ray_tracing_emission(
+        model, N_pix=args.N_pix, X_fov=args.X_FOV, freq_hz=args.freq, grid_n=args.grid_n, grid_extent=args.grid_extent,
+        z_observer=args.z_observer, dt=args.dt, n_steps=args.n_steps, record_stride=args.record_stride,
+        n_workers=args.workers, s_input_on=args.s_input_on, out_path=args.out_path, grff_lib=args.grff_lib, Nfreq=1,
+        freq0=args.freq, freq_log_step=0.0, save_plots=False, verbose=not args.quiet, device=args.device,
+        fallback_to_cpu=not args.no_fallback, raytrace_device=args.raytrace_device, grff_backend=args.grff_backend,
+        consider_beam=args.consider_beam, beam_fwhm=args.beam_fwhm, phi0_offset=args.phi0_offset, s_mode=args.s_mode)
+    if not args.quiet:
+        tb = res["emission_cube"]
+        print(f"T_b map {tb.shape} at {args.freq / 1e6:.1f} MHz: max {tb.max():.3e} K -> {args.out_path}")
+    return res
+
+
+if __name__ == "__main__":
+    main()

@@ -440,3 +440,34 @@ def test_render_map_theta_from_bvec_gr_on(oracle, session):
     assert np.abs(vi_ref).max() > 1e-3   # and polarises the map
     _cmp_maps(tb[0].reshape(N_pix, N_pix, 1), vi[0].reshape(N_pix, N_pix, 1), tb_ref.reshape(N_pix, N_pix, 1),
               vi_ref.reshape(N_pix, N_pix, 1))
+
+
+def test_workflow_command_line(tmp_path, oracle):
+    """The command line of script/resample_with_ray_tracing.py:652-730 (same flags) on a spherical model
+    file: cubes built on the GPU, map written with the reference's npz keys (:533-540), --consider-beam
+    adds the convolved map; --device cpu is refused (no CPU path)."""
+    from raytracinggrff_b200 import cubes, workflow
+    model = synthetic.spherical_corona(40, 30, 48, r_max=6.0)
+    path = tmp_path / "model.npz"
+    cubes.save_spherical_model(path, model)
+    out = tmp_path / "map.npz"
+    argv = ["-m", str(path), "-n", "12", "--grid-n", "48", "--n-steps", "2500", "--record-stride", "10", "-o", str(out),
+            "--device", "cuda", "--raytrace-device", "cuda", "--grff-backend", "fused", "--consider-beam",
+            "--beam-fwhm", "0.3", "--phi0-offset", "-30", "-q"]
+    res = workflow.main(argv)
+    z = np.load(out)
+    assert set(z.files) >= {"emission_cube", "emission_polVI_cube", "frequencies_Hz", "x_coords", "y_coords",
+                            "emission_map_beam"}
+    assert z["emission_cube"].shape == (12, 12, 1) and z["frequencies_Hz"][0] == 75e6
+    assert (z["emission_cube"] > 1e4).mean() > 0.4
+    # the same map through the per-pixel GET_MW backend
+    res2 = workflow.main(argv[:-8] + ["--grff-backend", "get_mw", "-q"])
+    _cmp_maps(res["emission_cube"], res["emission_polVI_cube"], res2["emission_cube"], res2["emission_polVI_cube"])
+    beam = res["emission_cube"][:, :, 0].copy()
+    beam[beam == 0] = np.nan
+    np.testing.assert_allclose(z["emission_map_beam"], oracle.gaussian_filter(beam, 0.3 / 2.88 * 12), rtol=1e-12,
+                               equal_nan=True)
+    with pytest.raises(RuntimeError):
+        workflow.main(argv[:-1] + ["--device", "cpu", "-q"])
+    with pytest.raises(FileNotFoundError):
+        workflow.main(["-m", str(tmp_path / "missing.npz"), "-q"])
