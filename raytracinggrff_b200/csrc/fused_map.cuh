@@ -176,26 +176,30 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_MINB) render_map_kernel(const Map
                 if (sample_valid(x, y, z, sv)) {
                     ++n_samples;
                     float3 bv = make_float3(0.f, 0.f, 0.f);
-                    const FieldSample f = BVEC ? sample_fields_bvec(a.fcube, a.bcube, a.fg, x, y, z, a.fill_ne, a.fill_te,
-                                                                    a.fill_b, bv)
-                                               : sample_fields(a.fcube, a.fg, x, y, z, a.fill_ne, a.fill_te, a.fill_b);
+                    FieldSample f = BVEC ? sample_fields_bvec_fast(a.fcube, a.bcube, a.fg, x, y, z, a.fill_ne, a.fill_te, bv)
+                                         : sample_fields(a.fcube, a.fg, x, y, z, a.fill_ne, a.fill_te, a.fill_b);
                     const float dist = first ? dist_first_np(x, y, z, px, py, pz) : dist_np(x, y, z, px, py, pz);
                     const float ds = __fmul_rn(dist, a.r_sun_cm);
+                    double cth = 6.123233995736766e-17, sth = 1.0;                          // theta = 90 deg
+                    if (BVEC) {
+                        // theta between the B vector and the propagation direction (towards the observer:
+                        // against the tracing direction), all from float32 inputs: FP32 throughout
+                        const float dx = x - px, dy = y - py, dz = z - pz;
+                        const float dn2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                        const float b2 = fmaf(bv.x, bv.x, fmaf(bv.y, bv.y, bv.z * bv.z));
+                        f.b = f.inb ? sqrtf(b2) : a.fill_b;
+                        if (b2 > 0.0f && dn2 > 0.0f) {
+                            const float inv = rsqrtf(b2 * dn2);
+                            const float c = -fmaf(bv.x, dx, fmaf(bv.y, dy, bv.z * dz)) * inv;
+                            cth = (double)fminf(1.0f, fmaxf(-1.0f, c));
+                            // sin from the cross product: no cancellation near theta = 0
+                            const float cx = bv.y * dz - bv.z * dy, cy = bv.z * dx - bv.x * dz, cz = bv.x * dy - bv.y * dx;
+                            sth = (double)fminf(1.0f, sqrtf(fmaf(cx, cx, fmaf(cy, cy, cz * cz))) * inv);
+                        }
+                    }
                     // --- Parms packing rules (script/resample_with_ray_tracing.py:472-501) ---
                     if (isfinite(f.ne) && isfinite(f.te) && isfinite(f.b)) {
-                        double cth = 6.123233995736766e-17, sth = 1.0, bmag = (double)f.b;   // theta = 90 deg
-                        if (BVEC) {
-                            const double dx = (double)x - (double)px, dy = (double)y - (double)py, dz = (double)z - (double)pz;
-                            const double dn2 = dx * dx + dy * dy + dz * dz;
-                            const double b2 = (double)bv.x * bv.x + (double)bv.y * bv.y + (double)bv.z * bv.z;
-                            bmag = sqrt(b2);
-                            if (b2 > 0.0 && dn2 > 0.0) {
-                                // radiation propagates towards the observer: against the tracing direction
-                                const double c = -((double)bv.x * dx + (double)bv.y * dy + (double)bv.z * dz) * rsqrt(b2 * dn2);
-                                cth = fmin(1.0, fmax(-1.0, c));
-                                sth = sqrt(fmax(0.0, 1.0 - cth * cth));
-                            }
-                        }
+                        const double bmag = (double)f.b;
                         Voxel vx = make_voxel_cs((double)ds, (double)f.te, (double)f.ne, bmag, cth, sth, a.em_flag, a.s_max);
                         // Parms[14] = S * area (script/resample_with_ray_tracing.py:501): source factor S
                         if (a.s_input) vx.scale = (double)sv;

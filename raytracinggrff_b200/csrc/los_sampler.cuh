@@ -128,6 +128,62 @@ __device__ __forceinline__ FieldSample sample_fields_bvec(const float4 *__restri
     return o;
 }
 
+// n_e, T (numpy-exact, as sample_fields) and the B vector at one point for the fused map's theta-aware
+// path.  The B vector has no numpy twin in the reference (theta from B.t is an extension), so its
+// three channels use fused lerps a + t (b - a) — a third of the arithmetic — and |B| comes from the
+// vector: the |B| channel of the field cube is not interpolated at all.  o.b = |B vector| (float32).
+__device__ __forceinline__ FieldSample sample_fields_bvec_fast(const float4 *__restrict__ fcube,
+                                                               const float4 *__restrict__ bcube, const GridGeomF &g,
+                                                               float px, float py, float pz, float fill_ne,
+                                                               float fill_te, float3 &bv)
+{
+    FieldSample o;
+    int i, j, k;
+    float tx, ty, tz;
+    o.inb = cell_of(g, px, py, pz, i, j, k, tx, ty, tz);
+    bv = make_float3(0.f, 0.f, 0.f);
+    o.b = 0.0f;
+    if (!o.inb) {
+        o.ne = fill_ne; o.te = fill_te;
+        return o;
+    }
+    const size_t sy = (size_t)g.nz, sx = (size_t)g.ny * g.nz;
+    const size_t off = (size_t)i * sx + (size_t)j * sy + (size_t)k;
+    const float2 tx2 = make_float2(tx, tx), ux2 = make_float2(__fsub_rn(1.0f, tx), __fsub_rn(1.0f, tx));
+    const float2 ty2 = make_float2(ty, ty), uy2 = make_float2(__fsub_rn(1.0f, ty), __fsub_rn(1.0f, ty));
+    const float2 tz2 = make_float2(tz, tz), uz2 = make_float2(__fsub_rn(1.0f, tz), __fsub_rn(1.0f, tz));
+#define RT_LO(c) make_float2((c).x, (c).y)
+#define RT_TRI_NP2(H)                                                                                         \
+    lerp_np2(lerp_np2(lerp_np2(H(c000), H(c100), ux2, tx2), lerp_np2(H(c010), H(c110), ux2, tx2), uy2, ty2),  \
+             lerp_np2(lerp_np2(H(c001), H(c101), ux2, tx2), lerp_np2(H(c011), H(c111), ux2, tx2), uy2, ty2), uz2, tz2)
+    {
+        const float4 *p = fcube + off;
+        const float4 c000 = __ldg(p), c001 = __ldg(p + 1), c010 = __ldg(p + sy), c011 = __ldg(p + sy + 1);
+        const float4 c100 = __ldg(p + sx), c101 = __ldg(p + sx + 1), c110 = __ldg(p + sx + sy),
+                     c111 = __ldg(p + sx + sy + 1);
+        const float2 nt = RT_TRI_NP2(RT_LO);
+        o.ne = nt.x; o.te = nt.y;
+    }
+#undef RT_TRI_NP2
+    {
+        const float4 *p = bcube + off;
+        const float4 c000 = __ldg(p), c001 = __ldg(p + 1), c010 = __ldg(p + sy), c011 = __ldg(p + sy + 1);
+        const float4 c100 = __ldg(p + sx), c101 = __ldg(p + sx + 1), c110 = __ldg(p + sx + sy),
+                     c111 = __ldg(p + sx + sy + 1);
+#define RT_FL2(a, b, t) __ffma2_rn(t, __fadd2_rn(b, make_float2(-(a).x, -(a).y)), a)
+#define RT_FL(a, b, t) fmaf(t, (b) - (a), a)
+        const float2 bxy = RT_FL2(RT_FL2(RT_FL2(RT_LO(c000), RT_LO(c100), tx2), RT_FL2(RT_LO(c010), RT_LO(c110), tx2), ty2),
+                                  RT_FL2(RT_FL2(RT_LO(c001), RT_LO(c101), tx2), RT_FL2(RT_LO(c011), RT_LO(c111), tx2), ty2), tz2);
+        bv.x = bxy.x; bv.y = bxy.y;
+        bv.z = RT_FL(RT_FL(RT_FL(c000.z, c100.z, tx), RT_FL(c010.z, c110.z, tx), ty),
+                     RT_FL(RT_FL(c001.z, c101.z, tx), RT_FL(c011.z, c111.z, tx), ty), tz);
+#undef RT_FL2
+#undef RT_FL
+    }
+#undef RT_LO
+    return o;
+}
+
 // B vector at a point (extension used by the theta-aware GR+FF path); zeros outside the cube.
 __device__ __forceinline__ float3 sample_bvec(const float4 *__restrict__ cube, const GridGeomF &g,
                                               float px, float py, float pz)

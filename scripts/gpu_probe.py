@@ -74,7 +74,11 @@ def main():
             print("tile order", tile)
         area = (2 * 1.44 / 512 * 6.957e10) ** 2
         freqs = synthetic.log_frequencies(75e6, 8, np.log10(20.0) / 7)
-        for label, kw in (("GR+FF bvec", dict(em_flag=4, use_bvec=True)), ("FF theta90", dict(em_flag=5, use_bvec=False))):
+        combos = (("GR+FF bvec", dict(em_flag=4, use_bvec=True)), ("FF theta90", dict(em_flag=5, use_bvec=False)))
+        if os.environ.get("RTGRFF_ALL_VARIANTS"):
+            combos += (("FF bvec", dict(em_flag=5, use_bvec=True)), ("GR+FF theta90", dict(em_flag=4, use_bvec=False)),
+                       ("GR+FF bvec no-cs", dict(em_flag=4, use_bvec=True, trace_crosssections=False)))
+        for label, kw in combos:
             tot = 0.0
             for f in freqs:
                 p = synthetic.frequency_scaled_params(float(f))
