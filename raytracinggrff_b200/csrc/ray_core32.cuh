@@ -250,17 +250,20 @@ __device__ __forceinline__ bool step32(const RayCube &C, const StepConst &K, Cel
             s.rx = fma((double)avx, K.c6, s.rx); s.ry = fma((double)avy, K.c6, s.ry); s.rz = fma((double)avz, K.c6, s.rz);
             cvx = avx; cvy = avy; cvz = avz;
             if (n_rays > 1) {
+                // norms through MUFU.RSQ (2 ulp): S is held to 1e-4, and the reference's +1e-32 / +1e-30
+                // guards only matter for a ray that did not move, whose S is NaN either way
                 const float dx = K.c6r * cvx, dy = K.c6r * cvy, dz = K.c6r * cvz;
-                const float nrd = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
-                const float inv = 1.0f / (nrd + 1e-32f);
+                const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                const float inv = rsqrtf(d2);
+                const float nrd = d2 * inv;
                 tx = dx * inv; ty = dy * inv; tz = dz * inv;
                 // reference axis: z if |t_z| < 0.9 else y (build_rays.py:188-194); e1 = a x t, e2 = t x e1
                 const bool use_z = fabsf(tz) < 0.9f;
                 float e1x = use_z ? -ty : tz, e1y = use_z ? tx : 0.0f, e1z = use_z ? 0.0f : -tx;
-                const float n1 = 1.0f / (sqrtf(fmaf(e1x, e1x, fmaf(e1y, e1y, e1z * e1z))) + 1e-30f);
+                const float n1 = rsqrtf(fmaf(e1x, e1x, fmaf(e1y, e1y, e1z * e1z)));
                 e1x *= n1; e1y *= n1; e1z *= n1;
                 e2x = ty * e1z - tz * e1y; e2y = tz * e1x - tx * e1z; e2z = tx * e1y - ty * e1x;
-                const float n2 = 1.0f / (sqrtf(fmaf(e2x, e2x, fmaf(e2y, e2y, e2z * e2z))) + 1e-30f);
+                const float n2 = rsqrtf(fmaf(e2x, e2x, fmaf(e2y, e2y, e2z * e2z)));
                 e2x *= n2; e2y *= n2; e2z *= n2;
                 eps = K.perturb * nrd;
                 ox = eps * e1x; oy = eps * e1y; oz = eps * e1z;
@@ -273,7 +276,7 @@ __device__ __forceinline__ bool step32(const RayCube &C, const StepConst &K, Cel
                 ox = eps * e2x; oy = eps * e2y; oz = eps * e2z;
             } else {
                 const float cx = d1y * ddz - d1z * ddy, cy = d1z * ddx - d1x * ddz, cz = d1x * ddy - d1y * ddx;
-                s_step = (double)(fabsf(fmaf(cx, tx, fmaf(cy, ty, cz * tz))) / (eps * eps));
+                s_step = (double)__fdividef(fabsf(fmaf(cx, tx, fmaf(cy, ty, cz * tz))), eps * eps);
             }
         }
     }

@@ -131,7 +131,8 @@ def test_trace_invariants_at_scale(session):
     expect_z = zs[None, :] - C_R * t[:, None]
     assert np.abs(r[..., 2] - expect_z).max() < 1e-11
     assert np.abs(r[..., 0] - xs[None]).max() == 0 and np.abs(r[..., 1] - ys[None]).max() == 0
-    assert np.abs(s - 1.0).max() < 1e-8
+    # the pencil basis is normalised with MUFU.RSQ (2 ulp): S = 1 to a few 1e-7 (tolerance on S: 1e-4)
+    assert np.abs(s - 1.0).max() < 2e-6
     assert act == steps * xs.size
     c = synthetic.corona_cube(n, 3.0)
     session.set_omega_cube(c["omega_pe"], c["x_grid"], c["y_grid"], c["z_grid"])
