@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_MINB) render_map_kernel(const Map
                     float3 bv = make_float3(0.f, 0.f, 0.f);
                     FieldSample f = BVEC ? sample_fields_bvec_fast(a.fcube, a.bcube, a.fg, x, y, z, a.fill_ne, a.fill_te, bv)
                                          : sample_fields(a.fcube, a.fg, x, y, z, a.fill_ne, a.fill_te, a.fill_b);
-                    const float dist = first ? dist_first_np(x, y, z, px, py, pz) : dist_np(x, y, z, px, py, pz);
+                    const float dist = first ? dist_first_np(x, y, z, px, py, pz) : dist_fast(x, y, z, px, py, pz);
                     const float ds = __fmul_rn(dist, a.r_sun_cm);
                     double cth = 6.123233995736766e-17, sth = 1.0;                          // theta = 90 deg
                     if (BVEC) {

@@ -187,25 +187,33 @@ __device__ __forceinline__ DiagOp voxel_op(const FreqC &f, const Voxel &v)
         const double us2 = u * s2;
         const double sD = sqrt(us2 * us2 + 4.0 * u * omv * omv * c2);
         const double num0 = us2 + 2.0 * omv * omv, base = 2.0 * omv - us2;
-        const double inv_sD = 1.0 / sD, us4 = us2 * us2, vo2 = 2.0 * vv * omv;
-        // n^2 = 1 - 2 v (1-v)/den,  F = 2 (num0 -+ us2^2/sD) / den^2  with den = base -+ sD: one reciprocal
-        // per mode and one shared 1/sD instead of four divisions, rsqrt instead of sqrt + divide
-        // X mode (sigma = -1): cut off for nu <= nu_B or v >= 1 - sqrt(u)
-        if (!(u >= 1.0 || vv >= 1.0 - sqrt(u))) {
-            const double inv_den = 1.0 / (base - sD);
-            const double n2 = 1.0 - vo2 * inv_den;
-            const double F = 2.0 * (num0 + us4 * inv_sD) * inv_den * inv_den;
+        const double us4 = us2 * us2, vo2 = 2.0 * vv * omv;
+        // n^2 = 1 - 2 v (1-v)/den,  F = 2 (num0 -+ us2^2/sD) / den^2  with den = base -+ sD.
+        // X mode (sigma = -1) is cut off for nu <= nu_B or v >= 1 - sqrt(u); below v = 1 that is
+        // sqrt(u) >= 1 - v  <=>  u >= (1-v)^2: no square root needed.  O mode (sigma = +1): v >= 1.
+        const bool x_on = !(u >= 1.0 || vv >= 1.0 || u >= omv * omv), o_on = vv < 1.0;
+        const double dX = base - sD, dO = base + sD;
+        double inv_sD, inv_dX, inv_dO;
+        if (FAST_T) {
+            // one reciprocal of the product instead of three reciprocals (a mode that is cut off lends 1)
+            const double a = x_on ? dX : 1.0, b = o_on ? dO : 1.0;
+            const double ab = a * b, r = 1.0 / (ab * sD);
+            inv_sD = r * ab; inv_dX = r * (b * sD); inv_dO = r * (a * sD);
+        } else {
+            inv_sD = 1.0 / sD; inv_dX = 1.0 / dX; inv_dO = 1.0 / dO;
+        }
+        if (x_on) {
+            const double n2 = 1.0 - vo2 * inv_dX;
+            const double F = 2.0 * (num0 + us4 * inv_sD) * inv_dX * inv_dX;
             if (n2 > 0.0 && isfinite(n2) && isfinite(F)) {
                 double kap = pref * F * rsqrt(n2);
                 if (!(kap > 0.0) || !isfinite(kap)) kap = 0.0;
                 slab_ab(true, kap * v.dz, n2 * srcb, aX, bX);
             }
         }
-        // O mode (sigma = +1): cut off for v >= 1
-        if (vv < 1.0) {
-            const double inv_den = 1.0 / (base + sD);
-            const double n2 = 1.0 - vo2 * inv_den;
-            const double F = 2.0 * (num0 - us4 * inv_sD) * inv_den * inv_den;
+        if (o_on) {
+            const double n2 = 1.0 - vo2 * inv_dO;
+            const double F = 2.0 * (num0 - us4 * inv_sD) * inv_dO * inv_dO;
             if (n2 > 0.0 && isfinite(n2) && isfinite(F)) {
                 double kap = pref * F * rsqrt(n2);
                 if (!(kap > 0.0) || !isfinite(kap)) kap = 0.0;
