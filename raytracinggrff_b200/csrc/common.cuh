@@ -88,6 +88,8 @@ struct rtgrff_ctx {
 
     // ray cube {omega_pe, d/dx, d/dy, d/dz}
     rtgrff::DevBuf wcube;
+    rtgrff::DevBuf pcube;            // cell-major polynomial form of wcube (8 float4 per cell), optional
+    bool has_pcube = false;
     rtgrff::GridGeom wgeom{};
     bool has_wcube = false;
 

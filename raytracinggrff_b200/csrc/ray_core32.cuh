@@ -52,15 +52,12 @@ struct Deriv32 {
 
 __device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
 
-// Fetch the 8 corners of the cell at element offset `off` and turn them into polynomial coefficients.
-__device__ __forceinline__ void load_cell(const RayCube &C, int off, Cell &c)
+// The 8 corners of a cell -> the coefficients of its trilinear polynomial, 8 float4
+// {l0,lz} {ly,lyz} {lx,lxz} {lxy,lxyz} {h0,hz} {hy,hyz} {hx,hxz} {hxy,hxyz}.
+__device__ __forceinline__ void cell_poly(const float4 &c000, const float4 &c001, const float4 &c010, const float4 &c011,
+                                          const float4 &c100, const float4 &c101, const float4 &c110, const float4 &c111,
+                                          Cell &c)
 {
-    const float4 *p = C.c + off;
-    const float4 c000 = __ldg(p), c001 = __ldg(p + 1);
-    const float4 c010 = __ldg(p + C.sy), c011 = __ldg(p + C.sy + 1);
-    const float4 c100 = __ldg(p + C.sx), c101 = __ldg(p + C.sx + 1);
-    const float4 c110 = __ldg(p + C.sx + C.sy), c111 = __ldg(p + C.sx + C.sy + 1);
-    c.off = off;
 #define RT_POLY(LO, a0, az, ay, ayz, ax, axz, axy, axyz)                                          \
     {                                                                                             \
         const float2 d00 = sub2(LO(c001), LO(c000)), d01 = sub2(LO(c011), LO(c010));              \
@@ -80,28 +77,78 @@ __device__ __forceinline__ void load_cell(const RayCube &C, int off, Cell &c)
 #undef RT_HI
 }
 
+// Make the cell at element offset `off` the cached one.  With the cell-major polynomial cube
+// (build_poly_cube_kernel) that is 8 LDG.128 from one 128-byte line; without it (cube too large to
+// afford 128 B per cell) the 8 corners are fetched from the node cube and differenced here.
+__device__ __forceinline__ void load_cell(const RayCube &C, int off, Cell &c)
+{
+    c.off = off;
+    if (C.pc) {
+        const float4 *p = C.pc + (size_t)off * 8;
+        const float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2), q3 = __ldg(p + 3);
+        const float4 q4 = __ldg(p + 4), q5 = __ldg(p + 5), q6 = __ldg(p + 6), q7 = __ldg(p + 7);
+#define RT_A(q) make_float2((q).x, (q).y)
+#define RT_B(q) make_float2((q).z, (q).w)
+        c.l0 = RT_A(q0); c.lz = RT_B(q0); c.ly = RT_A(q1); c.lyz = RT_B(q1);
+        c.lx = RT_A(q2); c.lxz = RT_B(q2); c.lxy = RT_A(q3); c.lxyz = RT_B(q3);
+        c.h0 = RT_A(q4); c.hz = RT_B(q4); c.hy = RT_A(q5); c.hyz = RT_B(q5);
+        c.hx = RT_A(q6); c.hxz = RT_B(q6); c.hxy = RT_A(q7); c.hxyz = RT_B(q7);
+#undef RT_A
+#undef RT_B
+        return;
+    }
+    const float4 *p = C.c + off;
+    cell_poly(__ldg(p), __ldg(p + 1), __ldg(p + C.sy), __ldg(p + C.sy + 1), __ldg(p + C.sx), __ldg(p + C.sx + 1),
+              __ldg(p + C.sx + C.sy), __ldg(p + C.sx + C.sy + 1), c);
+}
+
+// Node cube -> cell-major polynomial cube: cell (i,j,k), i < nx-1 etc., at [off*8, off*8+8) with the node
+// cube's offset off = (i*ny + j)*nz + k (the entries of the last node of each axis stay unused).
+__global__ void build_poly_cube_kernel(const float4 *__restrict__ nodes, float4 *__restrict__ pc, int nx, int ny, int nz)
+{
+    const int64_t nvox = (int64_t)nx * ny * nz;
+    const int sy = nz, sx = ny * nz;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nvox; q += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(q % nz), j = (int)((q / nz) % ny), i = (int)(q / sx);
+        if (i >= nx - 1 || j >= ny - 1 || k >= nz - 1) continue;
+        const float4 *p = nodes + q;
+        Cell c;
+        cell_poly(p[0], p[1], p[sy], p[sy + 1], p[sx], p[sx + 1], p[sx + sy], p[sx + sy + 1], c);
+        float4 *o = pc + q * 8;
+        o[0] = make_float4(c.l0.x, c.l0.y, c.lz.x, c.lz.y);     o[1] = make_float4(c.ly.x, c.ly.y, c.lyz.x, c.lyz.y);
+        o[2] = make_float4(c.lx.x, c.lx.y, c.lxz.x, c.lxz.y);   o[3] = make_float4(c.lxy.x, c.lxy.y, c.lxyz.x, c.lxyz.y);
+        o[4] = make_float4(c.h0.x, c.h0.y, c.hz.x, c.hz.y);     o[5] = make_float4(c.hy.x, c.hy.y, c.hyz.x, c.hyz.y);
+        o[6] = make_float4(c.hx.x, c.hx.y, c.hxz.x, c.hxz.y);   o[7] = make_float4(c.hxy.x, c.hxy.y, c.hxyz.x, c.hxyz.y);
+    }
+}
+
 // 0 <= t < 1 as one unsigned compare on the bit pattern (negative, NaN and -0 fail).
 __device__ __forceinline__ bool in_unit(float t) { return __float_as_uint(t) < 0x3f800000u; }
 
 // Slow path of an RHS evaluation: the point (tx,ty,tz) — coordinates relative to the cached cell —
-// lies outside it.  Moves the cache to the cell that holds the point (scipy bounds
-// g[0] <= x <= g[n-1]; the last node belongs to cell n-2 with t = 1), rebases the step's base
-// position (px,py,pz) and the point onto the new cell.  Returns false, leaving everything
-// untouched, when the point is outside the cube or not a number: that stage contributes a zero
-// derivative (build_rays.py:169-174).
-__device__ __forceinline__ bool move_cell(const RayCube &C, Cell &c, float &px, float &py, float &pz, float &tx,
-                                          float &ty, float &tz)
+// lies outside it.  Moves the cache to the cell that holds the point, rebases the step's base
+// position (px,py,pz) and the point onto the new cell.  `edge` (per step): the cached cell is within
+// three cells of a face, so a stage of this step may leave the cube — then the scipy bounds
+// g[0] <= x <= g[n-1] apply (the last node belongs to cell n-2 with t = 1) and the function returns
+// false, leaving everything untouched, for a point outside the cube: that stage contributes a zero
+// derivative (build_rays.py:169-174).  In the interior no stage can get out (a step moves every
+// stage by less than a cell, see step32) and the tests are skipped.  A NaN coordinate converts to
+// shift 0: the cell stays, the evaluation yields NaN and the stage is invalid.
+__device__ __forceinline__ bool move_cell(const RayCube &C, Cell &c, bool edge, float &px, float &py, float &pz,
+                                          float &tx, float &ty, float &tz)
 {
-    float fx = floorf(tx), fy = floorf(ty), fz = floorf(tz);
-    if (!((fx + fy) + fz == (fx + fy) + fz)) return false;                    // NaN coordinate
-    int ni = c.ci + (int)fx, nj = c.cj + (int)fy, nk = c.ck + (int)fz;
+    const int sx = __float2int_rd(tx), sy = __float2int_rd(ty), sz = __float2int_rd(tz);   // floor
+    int ni = c.ci + sx, nj = c.cj + sy, nk = c.ck + sz;
+    float fx = (float)sx, fy = (float)sy, fz = (float)sz;
     float ux = tx - fx, uy = ty - fy, uz = tz - fz;
-    if (ni == C.nx - 1 && ux == 0.0f) { ni = C.nx - 2; ux = 1.0f; fx -= 1.0f; }
-    if (nj == C.ny - 1 && uy == 0.0f) { nj = C.ny - 2; uy = 1.0f; fy -= 1.0f; }
-    if (nk == C.nz - 1 && uz == 0.0f) { nk = C.nz - 2; uz = 1.0f; fz -= 1.0f; }
-    if ((unsigned)ni > (unsigned)(C.nx - 2) || (unsigned)nj > (unsigned)(C.ny - 2) ||
-        (unsigned)nk > (unsigned)(C.nz - 2))
-        return false;
+    if (edge) {
+        if (ni == C.nx - 1 && ux == 0.0f) { ni = C.nx - 2; ux = 1.0f; fx -= 1.0f; }
+        if (nj == C.ny - 1 && uy == 0.0f) { nj = C.ny - 2; uy = 1.0f; fy -= 1.0f; }
+        if (nk == C.nz - 1 && uz == 0.0f) { nk = C.nz - 2; uz = 1.0f; fz -= 1.0f; }
+        if ((unsigned)ni > (unsigned)(C.nx - 2) || (unsigned)nj > (unsigned)(C.ny - 2) ||
+            (unsigned)nk > (unsigned)(C.nz - 2))
+            return false;
+    }
     const int off = (ni * C.ny + nj) * C.nz + nk;
     if (off != c.off) load_cell(C, off, c);
     c.ci = ni; c.cj = nj; c.ck = nk;
@@ -114,8 +161,8 @@ __device__ __forceinline__ bool move_cell(const RayCube &C, Cell &c, float &px, 
 // position (rebased when the cache moves), d the offset of this stage of this ray from it.  The
 // common case — the point is inside the cached cell — costs one range test; the cell change, the
 // bounds of the cube and the re-fetch all live on the slow path.
-__device__ __forceinline__ Deriv32 rhs32(const RayCube &C, Cell &cache, float &px, float &py, float &pz, float dx,
-                                         float dy, float dz, float kx, float ky, float kz)
+__device__ __forceinline__ Deriv32 rhs32(const RayCube &C, Cell &cache, bool edge, float &px, float &py, float &pz,
+                                         float dx, float dy, float dz, float kx, float ky, float kz)
 {
     Deriv32 d;
     d.vx = d.vy = d.vz = d.gx = d.gy = d.gz = 0.0f;
@@ -137,12 +184,12 @@ __device__ __forceinline__ Deriv32 rhs32(const RayCube &C, Cell &cache, float &p
     // evaluate on the cached cell before the range test resolves; the slow path re-evaluates
     RT_EVAL_POLY(wg, gg)
     if (!(in_unit(tx) & in_unit(ty) & in_unit(tz))) {
-        if (!move_cell(C, cache, px, py, pz, tx, ty, tz)) return d;
+        if (!move_cell(C, cache, edge, px, py, pz, tx, ty, tz)) return d;
         RT_EVAL_POLY(wg, gg)
     }
 #else
     if (!(in_unit(tx) & in_unit(ty) & in_unit(tz))) {
-        if (!move_cell(C, cache, px, py, pz, tx, ty, tz)) return d;
+        if (!move_cell(C, cache, edge, px, py, pz, tx, ty, tz)) return d;
     }
     RT_EVAL_POLY(wg, gg)
 #endif
@@ -209,11 +256,13 @@ __device__ __forceinline__ bool step32(const RayCube &C, const StepConst &K, Cel
         cache.ci = min((int)fx, C.nx - 2); cache.cj = min((int)fy, C.ny - 2); cache.ck = min((int)fz, C.nz - 2);
         load_cell(C, (cache.ci * C.ny + cache.cj) * C.nz + cache.ck, cache);
     }
-    // a step moves the ray by less than one cell and the cached cell is the cell of the last stage
-    // evaluated, so the master position is within two cells of it: it can only be outside the cube
-    // when the cached cell is that close to a face (exact scipy test there; a frozen ray stays here)
-    const bool edge = (cache.ci < 2) | (cache.ci > C.nx - 4) | (cache.cj < 2) | (cache.cj > C.ny - 4) |
-                      (cache.ck < 2) | (cache.ck > C.nz - 4);
+    // The cached cell is the cell of the last stage evaluated (previous step), within one cell of the
+    // previous master position; a step moves the master by less than a cell and every stage of this
+    // step lies within a cell of the new master: all cells this step can touch are within three of
+    // the cached one.  Only if that reaches a face can the master or a stage be outside the cube:
+    // exact scipy tests then (a frozen ray stays in this state), none in the interior.
+    const bool edge = (cache.ci < 3) | (cache.ci > C.nx - 5) | (cache.cj < 3) | (cache.cj > C.ny - 5) |
+                      (cache.ck < 3) | (cache.ck > C.nz - 5);
     if (edge && !in_cube(C, s.rx, s.ry, s.rz)) return false;
     // master position relative to the cached cell (FP64 -> FP32 once per step)
     float px = (float)(fx - (double)cache.ci), py = (float)(fy - (double)cache.cj), pz = (float)(fz - (double)cache.ck);
@@ -235,7 +284,7 @@ __device__ __forceinline__ bool step32(const RayCube &C, const StepConst &K, Cel
 #pragma unroll
 #endif
         for (int st = 0; st < 4; ++st) {
-            const Deriv32 d = rhs32(C, cache, px, py, pz, dx, dy, dz, skx, sky, skz);
+            const Deriv32 d = rhs32(C, cache, edge, px, py, pz, dx, dy, dz, skx, sky, skz);
             const float w = (st == 0 || st == 3) ? 1.0f : 2.0f;
             avx = fmaf(w, d.vx, avx); avy = fmaf(w, d.vy, avy); avz = fmaf(w, d.vz, avz);
             agx = fmaf(w, d.gx, agx); agy = fmaf(w, d.gy, agy); agz = fmaf(w, d.gz, agz);

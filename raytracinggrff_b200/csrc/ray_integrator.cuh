@@ -19,6 +19,7 @@ namespace rtgrff {
 
 struct RayCube {
     const float4 *__restrict__ c;
+    const float4 *__restrict__ pc;   // cell-major polynomial cube (ray_core32.cuh), 8 float4 per cell, or nullptr
     int nx, ny, nz;
     int sy, sx;  // element strides of y and x (z is contiguous)
     double x0, y0, z0, xl, yl, zl, idx, idy, idz;

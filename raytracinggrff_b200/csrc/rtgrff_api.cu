@@ -69,6 +69,7 @@ static RayCube ray_cube_of(const rtgrff_ctx *c)
     RayCube r;
     const GridGeom &g = c->wgeom;
     r.c = c->wcube.as<float4>();
+    r.pc = c->has_pcube ? c->pcube.as<float4>() : nullptr;
     r.nx = g.nx; r.ny = g.ny; r.nz = g.nz;
     r.sy = g.nz; r.sx = g.ny * g.nz;
     r.x0 = g.x0; r.y0 = g.y0; r.z0 = g.z0;
@@ -104,6 +105,28 @@ static int launched(rtgrff_ctx *c, const char *what)
     if (e != cudaSuccess) return fail(RTGRFF_ECUDA, "launch %s -> %s", what, cudaGetErrorString(e));
     return RTGRFF_OK;
 }
+
+// Cell-major polynomial cube for the FP32 stepper: 128 B per cell (8x the node cube).  Built when it
+// fits in a third of the free device memory (RTGRFF_POLY_CUBE=0 disables it, =1 forces it); the
+// stepper falls back to differencing the node cube on the fly without it.
+static int build_poly_cube(rtgrff_ctx *c, int nx, int ny, int nz)
+{
+    c->has_pcube = false;
+    const char *e = getenv("RTGRFF_POLY_CUBE");
+    if (e && e[0] == '0') return RTGRFF_OK;
+    const size_t bytes = (size_t)nx * ny * nz * 8 * sizeof(float4);
+    if (bytes > c->pcube.cap && !(e && e[0] == '1')) {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || bytes > free_b / 3) return RTGRFF_OK;
+    }
+    RT_TRY(c->pcube.reserve(bytes));
+    build_poly_cube_kernel<<<blocks_for((int64_t)nx * ny * nz, 256), 256, 0, c->stream>>>(c->wcube.as<float4>(),
+                                                                                         c->pcube.as<float4>(), nx, ny, nz);
+    RT_TRY(launched(c, "build_poly_cube_kernel"));
+    c->has_pcube = true;
+    return RTGRFF_OK;
+}
+
 
 static int cs_every_step()
 {
@@ -177,7 +200,7 @@ int rtgrff_ctx_destroy(rtgrff_ctx *c)
     if (!c) return RTGRFF_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf *bufs[] = {&c->wcube, &c->fcube, &c->bcube, &c->rec_pos, &c->rec_s, &c->smp_ne, &c->smp_te, &c->smp_b,
+    DevBuf *bufs[] = {&c->wcube, &c->pcube, &c->fcube, &c->bcube, &c->rec_pos, &c->rec_s, &c->smp_ne, &c->smp_te, &c->smp_b,
                       &c->smp_ds, &c->smp_s, &c->smp_valid, &c->in0, &c->in1, &c->in2, &c->in3, &c->out0, &c->out1,
                       &c->out2, &c->out3, &c->out4, &c->out5, &c->stage, &c->counters};
     for (DevBuf *b : bufs) b->release();
@@ -226,6 +249,7 @@ int rtgrff_set_omega_cube(rtgrff_ctx *c, const double *omega_pe, int nx, int ny,
     build_ray_cube_kernel<<<blocks_for((int64_t)nvox, 256), 256, 0, c->stream>>>(src, c->wcube.as<float4>(), nx, ny, nz,
                                                                                  geom[3], geom[7], geom[11]);
     RT_TRY(launched(c, "build_ray_cube_kernel"));
+    RT_TRY(build_poly_cube(c, nx, ny, nz));
     c->wgeom = g;
     c->has_wcube = true;
     RT_CUDA(cudaStreamSynchronize(c->stream));   // the host buffer may be reused by the caller
@@ -399,6 +423,7 @@ int rtgrff_compose_cubes(rtgrff_ctx *c, int want_bvec)
     build_ray_cube_kernel<<<blocks, 256, 0, c->stream>>>(c->stage.as<double>(), c->wcube.as<float4>(), nx, ny, nz,
                                                           geom[3], geom[7], geom[11]);
     RT_TRY(launched(c, "build_ray_cube_kernel"));
+    RT_TRY(build_poly_cube(c, nx, ny, nz));
     RT_CUDA(cudaStreamSynchronize(c->stream));
     c->wgeom = g; c->fgeom = g;
     GridGeomF &f = c->fgeomf;
