@@ -38,6 +38,7 @@ struct GridGeomF {
     int nx, ny, nz;
     float x0, y0, z0;
     float idx, idy, idz;
+    float fxl, fyl, fzl;   // (float)(n - 1): the in-bounds test 0 <= f <= n-1 of gpu_raytrace.py:505-511
 };
 
 extern thread_local char g_err[512];

@@ -88,7 +88,7 @@ struct RecordTransfer {
     {
         if (!v.ok) { have_prev = false; return; }
         if (NEED_BETWEEN) {
-            if (have_prev && prev.B > 0.0 && v.B > 0.0) st.apply(between_voxels(f, prev, v));
+            if (have_prev && prev.B > 0.0 && v.B > 0.0 && between_needed(f, prev, v)) st.apply(between_voxels(f, prev, v));
             prev = v;
             have_prev = true;
         }
@@ -103,7 +103,7 @@ struct OutwardTransferT : OutwardTransfer {
     {
         if (!v.ok) { have_prev = false; return; }
         if (NEED_BETWEEN) {
-            if (have_prev && prev.B > 0.0 && v.B > 0.0) {
+            if (have_prev && prev.B > 0.0 && v.B > 0.0 && between_needed(f, v, prev)) {
                 // radiation crosses v -> prev: between_voxels(v, prev) lists the events in that order,
                 // folding outwards meets them last-first
                 const Between b = between_voxels(f, v, prev);
@@ -187,20 +187,19 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_MINB) render_map_kernel(const Map
                         const float dx = x - px, dy = y - py, dz = z - pz;
                         const float dn2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
                         const float b2 = fmaf(bv.x, bv.x, fmaf(bv.y, bv.y, bv.z * bv.z));
-                        f.b = f.inb ? sqrtf(b2) : a.fill_b;
+                        f.b = f.inb ? sqrt_approx(b2) : a.fill_b;
                         if (b2 > 0.0f && dn2 > 0.0f) {
                             const float inv = rsqrtf(b2 * dn2);
                             const float c = -fmaf(bv.x, dx, fmaf(bv.y, dy, bv.z * dz)) * inv;
                             cth = (double)fminf(1.0f, fmaxf(-1.0f, c));
                             // sin from the cross product: no cancellation near theta = 0
                             const float cx = bv.y * dz - bv.z * dy, cy = bv.z * dx - bv.x * dz, cz = bv.x * dy - bv.y * dx;
-                            sth = (double)fminf(1.0f, sqrtf(fmaf(cx, cx, fmaf(cy, cy, cz * cz))) * inv);
+                            sth = (double)fminf(1.0f, sqrt_approx(fmaf(cx, cx, fmaf(cy, cy, cz * cz))) * inv);
                         }
                     }
                     // --- Parms packing rules (script/resample_with_ray_tracing.py:472-501) ---
                     if (isfinite(f.ne) && isfinite(f.te) && isfinite(f.b)) {
-                        const double bmag = (double)f.b;
-                        Voxel vx = make_voxel_cs((double)ds, (double)f.te, (double)f.ne, bmag, cth, sth, a.em_flag, a.s_max);
+                        Voxel vx = make_voxel_f(ds, f.te, f.ne, f.b, cth, sth, a.em_flag, a.s_max);
                         // Parms[14] = S * area (script/resample_with_ray_tracing.py:501): source factor S
                         if (a.s_input) vx.scale = (double)sv;
                         tr.push(fq, vx);

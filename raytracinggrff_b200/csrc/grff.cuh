@@ -72,6 +72,23 @@ __device__ __forceinline__ Voxel make_voxel_cs(double dz, double T, double ne, d
     return v;
 }
 
+// The same voxel from the float32 sampler outputs: the range tests run on the floats (a compare pair
+// each instead of FP64 classification), which is what the doubles are converted from.
+__device__ __forceinline__ Voxel make_voxel_f(float dz, float T, float ne, float B, double cth, double sth, int flag,
+                                              int smax)
+{
+    Voxel v;
+    v.dz = (double)dz; v.T = (double)T; v.ne = (double)ne; v.B = (double)B;
+    v.cth = cth; v.sth = sth;
+    v.scale = 1.0;
+    v.smax = smax;
+    v.gr_on = !(flag & 1);
+    v.ff_on = !(flag & 2);
+    v.ok = (dz > 0.0f) & (dz < INFINITY) & (T > 0.0f) & (T < INFINITY) & (ne > 0.0f) & (ne < INFINITY) & (B >= 0.0f) &
+           (B < INFINITY) & (fabs(cth) <= 1.0);
+    return v;
+}
+
 __device__ __forceinline__ Voxel make_voxel(double dz, double T, double ne, double B, double th_deg,
                                             int flag, int smax)
 {
@@ -266,6 +283,16 @@ struct Between {
     double Q;     // exact-coupling transmission exp(-delta)
     bool qt;
 };
+
+// Cheap test for "something happens between p and k" (a quasi-transverse layer or a gyroresonance
+// layer): the per-ray kernels call between_voxels only then.  Same conditions as its early exit.
+__device__ __forceinline__ bool between_needed(const FreqC &f, const Voxel &p, const Voxel &k)
+{
+    const bool qt = (p.cth * k.cth < 0.0);
+    const double smax = (double)min(p.smax, k.smax);
+    const bool gr = p.gr_on && k.gr_on && (p.B != k.B) && ((p.B * smax > f.sn) || (k.B * smax > f.sn));
+    return qt || gr;
+}
 
 __device__ __forceinline__ Between between_voxels(const FreqC &f, const Voxel &p, const Voxel &k)
 {

@@ -32,8 +32,7 @@ __device__ __forceinline__ bool cell_of(const GridGeomF &g, float px, float py, 
     const float fx = __fmul_rn(__fsub_rn(px, g.x0), g.idx);
     const float fy = __fmul_rn(__fsub_rn(py, g.y0), g.idy);
     const float fz = __fmul_rn(__fsub_rn(pz, g.z0), g.idz);
-    const bool inb = (fx >= 0.0f) && (fy >= 0.0f) && (fz >= 0.0f) && (fx <= (float)(g.nx - 1)) &&
-                     (fy <= (float)(g.ny - 1)) && (fz <= (float)(g.nz - 1));
+    const bool inb = (fx >= 0.0f) && (fy >= 0.0f) && (fz >= 0.0f) && (fx <= g.fxl) && (fy <= g.fyl) && (fz <= g.fzl);
     if (!inb) return false;
     i = min(max((int)floorf(fx), 0), g.nx - 2);
     j = min(max((int)floorf(fy), 0), g.ny - 2);
@@ -220,6 +219,13 @@ __device__ __forceinline__ float dist_fast(float ax, float ay, float az, float b
     const float dx = ax - bx, dy = ay - by, dz = az - bz;
     float r;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(dx, dx, fmaf(dy, dy, dz * dz))));
+    return r;
+}
+
+__device__ __forceinline__ float sqrt_approx(float v)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));     // MUFU.SQRT, 2 ulp
     return r;
 }
 

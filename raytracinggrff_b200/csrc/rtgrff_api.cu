@@ -287,6 +287,7 @@ int rtgrff_set_field_cubes(rtgrff_ctx *c, const float *ne, const float *te, cons
     f.nx = nx; f.ny = ny; f.nz = nz;
     f.x0 = (float)geom[0]; f.y0 = (float)geom[4]; f.z0 = (float)geom[8];
     f.idx = (float)(1.0 / geom[1]); f.idy = (float)(1.0 / geom[5]); f.idz = (float)(1.0 / geom[9]);
+    f.fxl = (float)(nx - 1); f.fyl = (float)(ny - 1); f.fzl = (float)(nz - 1);
     c->has_fcube = true;
     c->has_bvec = bvec;
     RT_CUDA(cudaStreamSynchronize(c->stream));
@@ -430,6 +431,7 @@ int rtgrff_compose_cubes(rtgrff_ctx *c, int want_bvec)
     f.nx = nx; f.ny = ny; f.nz = nz;
     f.x0 = (float)geom[0]; f.y0 = (float)geom[4]; f.z0 = (float)geom[8];
     f.idx = (float)(1.0 / geom[1]); f.idy = (float)(1.0 / geom[5]); f.idz = (float)(1.0 / geom[9]);
+    f.fxl = (float)(nx - 1); f.fyl = (float)(ny - 1); f.fzl = (float)(nz - 1);
     c->has_wcube = true; c->has_fcube = true; c->has_bvec = want_bvec != 0;
     return RTGRFF_OK;
 }
