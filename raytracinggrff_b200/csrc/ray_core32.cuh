@@ -208,6 +208,18 @@ __device__ __forceinline__ Deriv32 rhs32(const RayCube &C, Cell &cache, bool edg
     return d;
 }
 
+// Largest distance, in cells, between the master position of a step and any stage of any of its
+// three rays (|v| <= 1: a full step plus the pencil offset eps = perturb * step).  The FP32 stepper
+// works for any value (positions are relative to the cached cell, whole-cell shifts are exact); the
+// host keeps it below kMaxStageOffsetCells so that cell-relative coordinates stay small (FP32
+// precision) and falls back to the FP64 stepper beyond.
+constexpr double kMaxStageOffsetCells = 8.0;
+__host__ __device__ inline double max_stage_offset_cells(double dt, double perturb_ratio, double idx, double idy, double idz)
+{
+    const double i = fmax(idx, fmax(idy, idz));
+    return (1.0 + fabs(perturb_ratio)) * dt * kC_R * i;
+}
+
 // Per-launch float constants derived from dt and the grid (uniform across the grid).
 struct StepConst {
     float hx, hy, hz;     // 0.5*dt*C_R/dx : half-step position offset per unit v, in cells
@@ -216,6 +228,7 @@ struct StepConst {
     float ix, iy, iz;     // 1/dx          : R_sun -> cells
     double c6;            // dt/6*C_R in double: master-state increments
     float perturb;
+    int margin;           // cells around the cached cell a step can touch (see step32): 3 * ceil(max stage offset)
 };
 
 __host__ __device__ __forceinline__ StepConst make_step_const(const RayCube &C, double dt, double perturb_ratio)
@@ -228,15 +241,8 @@ __host__ __device__ __forceinline__ StepConst make_step_const(const RayCube &C, 
     k.c6r = (float)k.c6;
     k.ix = (float)C.idx; k.iy = (float)C.idy; k.iz = (float)C.idz;
     k.perturb = (float)perturb_ratio;
+    k.margin = 3 * (int)ceil(fmax(1e-9, max_stage_offset_cells(dt, perturb_ratio, C.idx, C.idy, C.idz)));
     return k;
-}
-
-// Largest |cell offset| any stage of any of the three rays of a step can have; the FP32 stepper
-// needs it < 1 (host-side dispatch, rtgrff_api.cu).
-inline double max_stage_offset_cells(double dt, double perturb_ratio, double idx, double idy, double idz)
-{
-    const double i = fmax(idx, fmax(idy, idz));
-    return (1.0 + fabs(perturb_ratio)) * dt * kC_R * i;
 }
 
 // One full step of the master state `s`: classic RK4 (build_rays.py:177-182) of the central ray
@@ -256,13 +262,15 @@ __device__ __forceinline__ bool step32(const RayCube &C, const StepConst &K, Cel
         cache.ci = min((int)fx, C.nx - 2); cache.cj = min((int)fy, C.ny - 2); cache.ck = min((int)fz, C.nz - 2);
         load_cell(C, (cache.ci * C.ny + cache.cj) * C.nz + cache.ck, cache);
     }
-    // The cached cell is the cell of the last stage evaluated (previous step), within one cell of the
-    // previous master position; a step moves the master by less than a cell and every stage of this
-    // step lies within a cell of the new master: all cells this step can touch are within three of
-    // the cached one.  Only if that reaches a face can the master or a stage be outside the cube:
-    // exact scipy tests then (a frozen ray stays in this state), none in the interior.
-    const bool edge = (cache.ci < 3) | (cache.ci > C.nx - 5) | (cache.cj < 3) | (cache.cj > C.ny - 5) |
-                      (cache.ck < 3) | (cache.ck > C.nz - 5);
+    // The cached cell is the cell of the last stage evaluated in the previous step, within m cells of
+    // the previous master position (m = ceil of the largest stage offset, 1 for the usual dt); a step
+    // moves the master by at most m cells and every stage of this step lies within m of the new
+    // master: all cells this step can touch are within K.margin = 3 m of the cached one.  Only if
+    // that reaches a face can the master or a stage be outside the cube: exact scipy tests then (a
+    // frozen ray stays in this state), none in the interior.
+    const int mg = K.margin;
+    const bool edge = (cache.ci < mg) | (cache.ci > C.nx - 2 - mg) | (cache.cj < mg) | (cache.cj > C.ny - 2 - mg) |
+                      (cache.ck < mg) | (cache.ck > C.nz - 2 - mg);
     if (edge && !in_cube(C, s.rx, s.ry, s.rz)) return false;
     // master position relative to the cached cell (FP64 -> FP32 once per step)
     float px = (float)(fx - (double)cache.ci), py = (float)(fy - (double)cache.cj), pz = (float)(fz - (double)cache.ck);

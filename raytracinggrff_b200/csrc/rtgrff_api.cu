@@ -474,9 +474,9 @@ int rtgrff_trace(rtgrff_ctx *c, int64_t n_rays, const double *x_start, const dou
     a.active_steps = c->counters.as<unsigned long long>();
     const dim3 grid(blocks_for(n_rays, RT_BLOCK)), block(RT_BLOCK);
     int l64 = trace_variant();
-    // the FP32 cell-relative stepper needs every stage within one cell of the step's base cell
+    // the FP32 cell-relative stepper keeps every stage within a few cells of the cached cell
     if (l64 == MODE_FAST32 &&
-        !(max_stage_offset_cells(dt, trace_cs ? perturb_ratio : 0.0, c->wgeom.idx, c->wgeom.idy, c->wgeom.idz) < 0.999))
+        !(max_stage_offset_cells(dt, trace_cs ? perturb_ratio : 0.0, c->wgeom.idx, c->wgeom.idy, c->wgeom.idz) < kMaxStageOffsetCells))
         l64 = MODE_F64;
     RT_CUDA(cudaEventRecord(c->ev0, c->stream));
 #define RT_TRACE_CASE(v, CS, M) \
@@ -738,7 +738,7 @@ int rtgrff_render_map(rtgrff_ctx *c, int64_t n_rays, const double *x_start, cons
     int mode = trace_variant() == 0 ? MODE_FAST32 : MODE_F64;
     for (int f = 0; f < n_freq; ++f)
         if (!(max_stage_offset_cells(freqs[f].dt, trace_cs ? perturb_ratio : 0.0, c->wgeom.idx, c->wgeom.idy,
-                                     c->wgeom.idz) < 0.999))
+                                     c->wgeom.idz) < kMaxStageOffsetCells))
             mode = MODE_F64;
     // the per-frequency constants travel in the kernel parameters: kMaxFreqPerLaunch frequencies per launch
     for (int f0 = 0; f0 < n_freq; f0 += kMaxFreqPerLaunch) {

@@ -472,3 +472,30 @@ def test_workflow_command_line(tmp_path, oracle):
         workflow.main(argv[:-1] + ["--device", "cpu", "-q"])
     with pytest.raises(FileNotFoundError):
         workflow.main(["-m", str(tmp_path / "missing.npz"), "-q"])
+
+
+def test_trace_steps_longer_than_a_cell(oracle, session):
+    """Low-frequency presets on a fine cube make a step (plus the pencil offset) span more than one
+    cell (BASELINE config 5 at 20-24 MHz: 1.1 cells).  The FP32 stepper handles whole-cell shifts of
+    any size; the face margin grows with the step (StepConst.margin)."""
+    n = 160
+    g = np.linspace(-1.2, 1.2, n)
+    X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
+    r = np.sqrt(X ** 2 + Y ** 2 + Z ** 2)
+    w = 2 * np.pi * 45e6 * np.exp(-(r - 0.3)) * (1 + 0.2 * np.sin(3 * X) * np.cos(2 * Y))
+    session.set_omega_cube(w, g, g, g)
+    rng = np.random.default_rng(21)
+    m = 64
+    xs, ys = rng.uniform(-0.9, 0.9, m), rng.uniform(-0.9, 0.9, m)
+    zs = np.full(m, 1.2)
+    zs[:4] = [1.2000001, 1.19, 1.0, 0.5]
+    kv = np.column_stack([rng.normal(scale=0.15, size=m), rng.normal(scale=0.15, size=m), -np.ones(m)])
+    kv /= np.linalg.norm(kv, axis=1, keepdims=True)
+    for dt, steps in ((0.0134, 500), (0.03, 260)):       # 1.15 and 2.6 cells per (step + pencil)
+        cells = 3 * dt * (2.998e10 / 6.96e10) * (n - 1) / 2.4
+        assert cells > 1.1
+        rr, ss, act = session.trace(80e6, xs, ys, zs, kv, dt, steps, 7, True, 2.0)
+        r_ref, cs_ref, act_ref = oracle.ray_trace(w, g, g, g, 80e6, xs, ys, zs, kv, dt, steps, 7, True, perturb_ratio=2,
+                                                  return_active=True)
+        _cmp_paths(rr, ss, r_ref, np.array(cs_ref), lo=np.full(3, -1.2), hi=np.full(3, 1.2), step_len=1.01 * dt * 0.43075)
+        assert abs(act - act_ref) <= 2
