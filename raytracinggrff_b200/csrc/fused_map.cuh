@@ -50,16 +50,31 @@ struct MapArgs {
     unsigned long long *active_steps;    // [0] active central steps, [1] steps with the pencil traced, [2] valid samples
 };
 
+// The float32 values a voxel is built from.  The transfer keeps the previous non-empty voxel in this
+// form — 6 registers live across the stepper instead of the 17 of a Voxel — and rebuilds the Voxel on
+// the rare occasions something happens between two voxels.
+struct VoxLite {
+    float dz, T, ne, B, cth, scale;
+};
+
+__device__ __forceinline__ Voxel voxel_of(const VoxLite &l, int flag, int smax)
+{
+    Voxel v = make_voxel_f(l.dz, l.T, l.ne, l.B, (double)l.cth, sqrt(fmax(0.0, 1.0 - (double)l.cth * (double)l.cth)),
+                           flag, smax);
+    v.scale = (double)l.scale;
+    return v;
+}
+
 // Transfer accumulated from the observer outwards (RTGRFF_ORDER_REVERSED): the records arrive
 // nearest-first, the radiation travels farthest-first.  I_obs = acc + M I_far with M a 2x2 matrix
 // in (L,R); folding one more (farther) operator I -> A I + b gives acc += M b, M = M A.
 struct OutwardTransfer {
     double m00, m01, m10, m11, accL, accR;
-    Voxel prev;
+    VoxLite prev;
     bool have_prev;
     __device__ __forceinline__ void init()
     {
-        m00 = m11 = 1.0; m01 = m10 = 0.0; accL = accR = 0.0; have_prev = false; prev.ok = false;
+        m00 = m11 = 1.0; m01 = m10 = 0.0; accL = accR = 0.0; have_prev = false;
     }
     __device__ __forceinline__ void fold(const DiagOp &d)
     {
@@ -81,15 +96,16 @@ struct OutwardTransfer {
 template <bool NEED_BETWEEN>
 struct RecordTransfer {
     PolState<1> st;
-    Voxel prev;
+    VoxLite prev;
     bool have_prev;
-    __device__ __forceinline__ void init() { st.clear(); have_prev = false; prev.ok = false; }
-    __device__ __forceinline__ void push(const FreqC &f, const Voxel &v)
+    __device__ __forceinline__ void init() { st.clear(); have_prev = false; }
+    __device__ __forceinline__ void push(const FreqC &f, const Voxel &v, const VoxLite &l, int flag, int smax)
     {
         if (!v.ok) { have_prev = false; return; }
         if (NEED_BETWEEN) {
-            if (have_prev && prev.B > 0.0 && v.B > 0.0 && between_needed(f, prev, v)) st.apply(between_voxels(f, prev, v));
-            prev = v;
+            if (have_prev && prev.B > 0.0f && l.B > 0.0f && between_needed_f(f, prev.cth, prev.B, l.cth, l.B, smax, v.gr_on))
+                st.apply(between_voxels(f, voxel_of(prev, flag, smax), v));
+            prev = l;
             have_prev = true;
         }
         st.apply(voxel_op<true>(f, v));
@@ -99,19 +115,19 @@ struct RecordTransfer {
 
 template <bool NEED_BETWEEN>
 struct OutwardTransferT : OutwardTransfer {
-    __device__ __forceinline__ void push(const FreqC &f, const Voxel &v)
+    __device__ __forceinline__ void push(const FreqC &f, const Voxel &v, const VoxLite &l, int flag, int smax)
     {
         if (!v.ok) { have_prev = false; return; }
         if (NEED_BETWEEN) {
-            if (have_prev && prev.B > 0.0 && v.B > 0.0 && between_needed(f, v, prev)) {
+            if (have_prev && prev.B > 0.0f && l.B > 0.0f && between_needed_f(f, l.cth, l.B, prev.cth, prev.B, smax, v.gr_on)) {
                 // radiation crosses v -> prev: between_voxels(v, prev) lists the events in that order,
                 // folding outwards meets them last-first
-                const Between b = between_voxels(f, v, prev);
+                const Between b = between_voxels(f, v, voxel_of(prev, flag, smax));
                 fold(b.after);
                 if (b.qt) fold_qt(b.Q);
                 fold(b.before);
             }
-            prev = v;
+            prev = l;
             have_prev = true;
         }
         fold(voxel_op<true>(f, v));
@@ -150,9 +166,10 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_MINB) render_map_kernel(const Map
     bool alive = has_ray;
     double s_step = CS ? 0.0 : 1.0, s_cum = 1.0;
     const bool cumulative = CS && a.s_mode == RTGRFF_S_CUMULATIVE;
-    unsigned long long moved_steps = 0;
-    unsigned int pencil_steps = 0, n_samples = 0;
-    int64_t next_rec = 0;
+    unsigned int n_samples = 0;
+    const int n_steps = (int)fp.n_steps, stride = (int)fp.stride;     // < 2^31, checked on the host
+    int next_rec = 0;
+    int death = -1;                       // step at which the ray froze (-1: still moving)
 
     typename std::conditional<ORDER == RTGRFF_ORDER_RECORD, RecordTransfer<NEED_BETWEEN>,
                               OutwardTransferT<NEED_BETWEEN>>::type tr;
@@ -160,16 +177,15 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_MINB) render_map_kernel(const Map
     bool first = true;
     bool tail_done = !has_ray;            // a frozen ray repeats the same record: ds = 0 -> empty voxel
 
-    for (int64_t i = 0; i < fp.n_steps; ++i) {
+    for (int i = 0; i < n_steps; ++i) {
         if (alive) {
             const bool want_s = CS && (i == next_rec || a.cs_every_step || cumulative);
             alive = advance_ray<CS, MODE>(C, K, cache, s, fp.dt, a.perturb_ratio, want_s, s_step);
             if (cumulative) s_cum *= s_step;     // gpu_raytrace.py:398-408
-            moved_steps += alive ? 1ull : 0ull;
-            pencil_steps += (want_s && alive) ? 1u : 0u;
+            if (!alive) death = i;
         }
         if (i == next_rec) {
-            next_rec += fp.stride;
+            next_rec += stride;
             if (!tail_done) {
                 // --- sampler (float32, gpu_raytrace.py:642-650) ---
                 const float x = (float)s.rx, y = (float)s.ry, z = (float)s.rz, sv = (float)(cumulative ? s_cum : s_step);
@@ -180,7 +196,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_MINB) render_map_kernel(const Map
                                          : sample_fields(a.fcube, a.fg, x, y, z, a.fill_ne, a.fill_te, a.fill_b);
                     const float dist = first ? dist_first_np(x, y, z, px, py, pz) : dist_fast(x, y, z, px, py, pz);
                     const float ds = __fmul_rn(dist, a.r_sun_cm);
-                    double cth = 6.123233995736766e-17, sth = 1.0;                          // theta = 90 deg
+                    float cthf = 6.123233995736766e-17f, sthf = 1.0f;                       // theta = 90 deg
                     if (BVEC) {
                         // theta between the B vector and the propagation direction (towards the observer:
                         // against the tracing direction), all from float32 inputs: FP32 throughout
@@ -191,18 +207,20 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_MINB) render_map_kernel(const Map
                         if (b2 > 0.0f && dn2 > 0.0f) {
                             const float inv = rsqrtf(b2 * dn2);
                             const float c = -fmaf(bv.x, dx, fmaf(bv.y, dy, bv.z * dz)) * inv;
-                            cth = (double)fminf(1.0f, fmaxf(-1.0f, c));
+                            cthf = fminf(1.0f, fmaxf(-1.0f, c));
                             // sin from the cross product: no cancellation near theta = 0
                             const float cx = bv.y * dz - bv.z * dy, cy = bv.z * dx - bv.x * dz, cz = bv.x * dy - bv.y * dx;
-                            sth = (double)fminf(1.0f, sqrt_approx(fmaf(cx, cx, fmaf(cy, cy, cz * cz))) * inv);
+                            sthf = fminf(1.0f, sqrt_approx(fmaf(cx, cx, fmaf(cy, cy, cz * cz))) * inv);
                         }
                     }
                     // --- Parms packing rules (script/resample_with_ray_tracing.py:472-501) ---
                     if (isfinite(f.ne) && isfinite(f.te) && isfinite(f.b)) {
-                        Voxel vx = make_voxel_f(ds, f.te, f.ne, f.b, cth, sth, a.em_flag, a.s_max);
                         // Parms[14] = S * area (script/resample_with_ray_tracing.py:501): source factor S
-                        if (a.s_input) vx.scale = (double)sv;
-                        tr.push(fq, vx);
+                        const VoxLite lite = {ds, f.te, f.ne, f.b, cthf, a.s_input ? sv : 1.0f};
+                        Voxel vx = make_voxel_f(ds, f.te, f.ne, f.b, BVEC ? (double)cthf : 6.123233995736766e-17,
+                                                (double)sthf, a.em_flag, a.s_max);
+                        vx.scale = (double)lite.scale;
+                        tr.push(fq, vx, lite, a.em_flag, a.s_max);
                     }
                     px = x; py = y; pz = z;
                     first = false;
@@ -221,6 +239,10 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_MINB) render_map_kernel(const Map
         a.vi[(size_t)(a.freq_base + fi) * a.n_rays + ray] = vi;
     }
     if (a.active_steps) {
+        // a ray moves on steps [0, death): the counters follow from where it froze
+        unsigned long long moved_steps = has_ray ? (unsigned long long)(death >= 0 ? death : n_steps) : 0ull;
+        const unsigned long long pencil_steps =
+            !CS ? 0ull : ((a.cs_every_step || cumulative) ? moved_steps : (moved_steps + stride - 1) / stride);
         unsigned long long ps = pencil_steps, ns = n_samples;
         for (int off = 16; off > 0; off >>= 1) {
             moved_steps += __shfl_down_sync(0xffffffffu, moved_steps, off);

@@ -161,6 +161,7 @@ struct FreqC {
     double nu, nu2, inv_nu2, ln_nu;
     double sn;    // kBres * nu: resonant field of harmonic s is sn / s
     double kff;   // kKff * kZeta / nu^2: free-free opacity prefactor
+    float snf;    // sn rounded up to float32 (conservative side of between_needed_f)
 };
 
 __host__ __device__ __forceinline__ FreqC make_freq(double nu)
@@ -169,6 +170,7 @@ __host__ __device__ __forceinline__ FreqC make_freq(double nu)
     f.nu = nu; f.nu2 = nu * nu; f.inv_nu2 = 1.0 / f.nu2; f.ln_nu = log(nu);
     f.sn = kBres * nu;
     f.kff = kKff * kZeta * f.inv_nu2;
+    f.snf = (float)(f.sn * (1.0 - 1e-6));
     return f;
 }
 
@@ -291,6 +293,16 @@ __device__ __forceinline__ bool between_needed(const FreqC &f, const Voxel &p, c
     const bool qt = (p.cth * k.cth < 0.0);
     const double smax = (double)min(p.smax, k.smax);
     const bool gr = p.gr_on && k.gr_on && (p.B != k.B) && ((p.B * smax > f.sn) || (k.B * smax > f.sn));
+    return qt || gr;
+}
+
+// The same test on the float32 values the voxels were built from (the per-ray kernels keep the previous
+// voxel as six floats); the resonance test leans to the "needed" side by 1e-6, between_voxels decides.
+__device__ __forceinline__ bool between_needed_f(const FreqC &f, float p_cth, float p_B, float k_cth, float k_B,
+                                                 int smax, bool gr_on)
+{
+    const bool qt = (p_cth * k_cth < 0.0f);
+    const bool gr = gr_on && (p_B != k_B) && (fmaxf(p_B, k_B) * (float)smax > f.snf);
     return qt || gr;
 }
 

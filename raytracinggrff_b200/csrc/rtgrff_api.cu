@@ -682,7 +682,8 @@ int rtgrff_render_map(rtgrff_ctx *c, int64_t n_rays, const double *x_start, cons
     std::vector<FreqDev> fd(n_freq);
     int64_t nominal = 0;
     for (int f = 0; f < n_freq; ++f) {
-        if (freqs[f].n_steps < 0 || freqs[f].record_stride < 1 || !(freqs[f].freq_hz > 0.0))
+        if (freqs[f].n_steps < 0 || freqs[f].record_stride < 1 || !(freqs[f].freq_hz > 0.0) ||
+            freqs[f].n_steps > 2147483000 || freqs[f].record_stride > 2147483000)
             return fail(RTGRFF_EINVAL, "bad per-frequency parameters at index %d", f);
         fd[f].nu = freqs[f].freq_hz;
         fd[f].omega0 = 2.0 * M_PI * freqs[f].freq_hz;

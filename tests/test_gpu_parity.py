@@ -370,6 +370,14 @@ def test_render_map_multi_frequency_and_orders(oracle, session):
     assert tb.shape == (3, N_pix * N_pix)
     assert stats["nominal_ray_steps"] == sum(p["n_steps"] for p in fps) * xs.size
     assert 0 < stats["active_ray_steps"] <= stats["nominal_ray_steps"]
+    # the counters of the fused kernel (derived from the step at which each ray froze) equal the trace kernel's
+    act_sum = pen_sum = 0
+    for p in fps:
+        _, _, act = session.trace(p["freq_hz"], xs, ys, zs, kv, p["dt"], p["n_steps"], p["record_stride"], True, 2.0,
+                                  fetch=False)
+        act_sum += act
+    assert stats["active_ray_steps"] == act_sum
+    assert 0 < stats["pencil_steps"] <= stats["active_ray_steps"] and stats["valid_samples"] <= stats["pencil_steps"]
     for i, p in enumerate(fps):
         tb_ref, vi_ref, _ = _oracle_chain(oracle, c, N_pix, X_fov, 3.0, p["freq_hz"], p["dt"], p["n_steps"],
                                           p["record_stride"])
