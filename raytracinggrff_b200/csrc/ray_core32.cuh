@@ -1,35 +1,30 @@
-// Ray stepper v3 for sm_100a: FP64 master state, FP32 cell-relative RHS, register cell cache held
-// as the cell's trilinear POLYNOMIAL, packed FP32x2 (FFMA2) evaluation, one RHS body in the binary.
+// Ray stepper for sm_100a: FP64 master state, FP32 RHS relative to the CACHED CELL, the cell held in
+// registers as its trilinear POLYNOMIAL (fed from a cell-major polynomial cube), packed FP32x2 (FFMA2).
 //
-// Same mathematics as ray_integrator.cuh (build_rays.py:158-239) reorganised around what ncu showed.
-// profiles/r1a_trace_rays_kernel_*.txt (FP64 stepper): ~2500 instructions per ray-step at 49 %
-// issue utilisation, L1 data pipe 65 % (8 x LDG.128 per RHS), FP64 pipe 29 %, XU pipe 29 %.
-// profiles/r1d_render_map_kernel_c4_bench.txt (stepper v2, RK4 stages and EDGE/interior variants
-// all inlined: 16 copies of the RHS, 134 KB of SASS): 30 % of all stall samples are `no_inst` —
-// the 32 KB instruction cache thrashes — and 4 % of the instructions are local-memory spills.
+// Same mathematics as ray_integrator.cuh (build_rays.py:158-239) reorganised around what ncu showed
+// (DESIGN.md 4.1 has the sequence; profiles/r1a_*, r1d_*, r1f_*):
 //
 //  * The ray's position and wave vector stay FP64 (the "master" state): every step adds
 //    (double)sum * (dt/6 * C_R), so the accumulation over thousands of steps is exact to 1e-16
 //    and no rounded constant multiplies the accumulated path.
-//  * Within a step everything is FP32 and CELL-RELATIVE: the master position is split once per
-//    step into (base cell, fraction in [0,1)); the four RK4 stages and the two cross-section
-//    rays are small float offsets from that cell (the host falls back to the FP64 stepper when
-//    a step could span a whole cell).  Cell fractions carry 6e-8 of a cell (~1e-9 R_sun), the
-//    corners are FP32 anyway, omega = sqrt(w^2+k^2) and the derivatives need 1e-7 relative:
-//    increments are ~1e-3 R_sun, so the per-step error is ~1e-10 R_sun and random.
-//  * The current cell lives in 32 registers as the coefficients of its trilinear polynomial
+//  * Within a step everything is FP32 and relative to the cached cell: the master position is
+//    converted once per step, the four RK4 stages and the two cross-section rays are float
+//    offsets from it.  Cell fractions carry 6e-8 of a cell (~1e-9 R_sun), the corners are FP32
+//    anyway, omega = sqrt(w^2+k^2) and the derivatives need 1e-7 relative: increments are
+//    ~1e-3 R_sun, so the per-step error is ~1e-10 R_sun and random.
+//  * The cached cell lives in 32 registers as the coefficients of its trilinear polynomial
 //        f = (a0 + az z) + y (ay + ayz z) + x ((ax + axz z) + y (axy + axyz z))
 //    for the channel pairs {omega_pe, d/dx} and {d/dy, d/dz}: one RHS is 14 packed FFMA2 with a
-//    dependency depth of 3 (the nested-lerp form is 14 FMUL2 + 14 FFMA2, depth 6).  A stage whose
-//    cell differs from the cached one re-fetches the 8 corners with LDG.128 (only the lanes that
-//    moved generate L1 wavefronts) and differences them once (24 FADD2).  A ray spends ~10-35
-//    steps x up to 12 RHS evaluations in one cell.
-//  * ONE copy of the RHS in the binary: the 4 RK4 stages and the 3 rays of a step (central + the
-//    two pencil rays) are rolled loops around it, and the face handling is a run-time flag
-//    instead of a template variant, so the whole stepper is ~600 instructions (< 10 KB) and the
-//    hot loop of the fused kernel fits the instruction cache.
-//  * Away from the cube faces no stage can leave the cube, so the per-stage bounds test is
-//    one test of the base cell per step (`edge`); the exact scipy bounds run near the faces only.
+//    dependency depth of 3 (nested lerps: 14 FMUL2 + 14 FFMA2, depth 6).
+//  * Fast path of an RHS = one range test (VIMNMX3.U32 + ISETP on the bit patterns: 0 <= t < 1)
+//    + the evaluation, ~55 instructions.  Everything else — leaving the cell, the cube bounds,
+//    the re-fetch — is the slow path (move_cell), which 1-5 of a warp's 32 lanes take at a time:
+//    it is kept short by the polynomial cube (8 LDG.128 from one 128-byte line, no differencing)
+//    and by a per-step `edge` flag that drops the bounds logic in the interior.
+//  * One RHS body per RK4 stage (the stage loop is unrolled: constant weights), the three rays
+//    of a step (central + two pencil rays) are a rolled loop, the face handling is a run-time
+//    flag: the stepper is ~1500 SASS instructions where the first version (16 inlined copies of
+//    the RHS, 134 KB of SASS) lost 30 % of its issue slots to instruction-cache misses.
 #pragma once
 
 #include "ray_integrator.cuh"
@@ -167,33 +162,18 @@ __device__ __forceinline__ Deriv32 rhs32(const RayCube &C, Cell &cache, bool edg
     Deriv32 d;
     d.vx = d.vy = d.vz = d.gx = d.gy = d.gz = 0.0f;
     float tx = px + dx, ty = py + dy, tz = pz + dz;
-#define RT_EVAL_POLY(wg, gg)                                                                                    \
-    {                                                                                                           \
-        const float2 tz2 = make_float2(tz, tz), ty2 = make_float2(ty, ty), tx2 = make_float2(tx, tx);           \
-        /* {omega_pe, d/dx} */                                                                                  \
-        wg = __ffma2_rn(                                                                                        \
-            __ffma2_rn(__ffma2_rn(cache.lxyz, tz2, cache.lxy), ty2, __ffma2_rn(cache.lxz, tz2, cache.lx)), tx2, \
-            __ffma2_rn(__ffma2_rn(cache.lyz, tz2, cache.ly), ty2, __ffma2_rn(cache.lz, tz2, cache.l0)));        \
-        /* {d/dy, d/dz} */                                                                                      \
-        gg = __ffma2_rn(                                                                                        \
-            __ffma2_rn(__ffma2_rn(cache.hxyz, tz2, cache.hxy), ty2, __ffma2_rn(cache.hxz, tz2, cache.hx)), tx2, \
-            __ffma2_rn(__ffma2_rn(cache.hyz, tz2, cache.hy), ty2, __ffma2_rn(cache.hz, tz2, cache.h0)));        \
-    }
-    float2 wg, gg;
-#ifdef RT_SPECULATE
-    // evaluate on the cached cell before the range test resolves; the slow path re-evaluates
-    RT_EVAL_POLY(wg, gg)
-    if (!(in_unit(tx) & in_unit(ty) & in_unit(tz))) {
-        if (!move_cell(C, cache, edge, px, py, pz, tx, ty, tz)) return d;
-        RT_EVAL_POLY(wg, gg)
-    }
-#else
     if (!(in_unit(tx) & in_unit(ty) & in_unit(tz))) {
         if (!move_cell(C, cache, edge, px, py, pz, tx, ty, tz)) return d;
     }
-    RT_EVAL_POLY(wg, gg)
-#endif
-#undef RT_EVAL_POLY
+    const float2 tz2 = make_float2(tz, tz), ty2 = make_float2(ty, ty), tx2 = make_float2(tx, tx);
+    // {omega_pe, d/dx}
+    const float2 wg = __ffma2_rn(
+        __ffma2_rn(__ffma2_rn(cache.lxyz, tz2, cache.lxy), ty2, __ffma2_rn(cache.lxz, tz2, cache.lx)), tx2,
+        __ffma2_rn(__ffma2_rn(cache.lyz, tz2, cache.ly), ty2, __ffma2_rn(cache.lz, tz2, cache.l0)));
+    // {d/dy, d/dz}
+    const float2 gg = __ffma2_rn(
+        __ffma2_rn(__ffma2_rn(cache.hxyz, tz2, cache.hxy), ty2, __ffma2_rn(cache.hxz, tz2, cache.hx)), tx2,
+        __ffma2_rn(__ffma2_rn(cache.hyz, tz2, cache.hy), ty2, __ffma2_rn(cache.hz, tz2, cache.h0)));
     const float w = wg.x;
     const float om2 = fmaf(w, w, fmaf(kx, kx, fmaf(ky, ky, kz * kz)));
     // valid = isfinite(omega_pe) & isfinite(omega) & (omega > 0)   (build_rays.py:169); a non-finite
@@ -286,11 +266,7 @@ __device__ __forceinline__ bool step32(const RayCube &C, const StepConst &K, Cel
         const float qx = ox * K.ix, qy = oy * K.iy, qz = oz * K.iz;    // start of this ray relative to p, cells
         float dx = qx, dy = qy, dz = qz, skx = kx, sky = ky, skz = kz;
         float avx = 0.0f, avy = 0.0f, avz = 0.0f, agx = 0.0f, agy = 0.0f, agz = 0.0f;   // k1 + 2 k2 + 2 k3 + k4
-#ifdef RT_STAGE_ROLLED
-#pragma unroll 1
-#else
-#pragma unroll
-#endif
+#pragma unroll          // the four stages unrolled (constant weights), the three rays of a step rolled
         for (int st = 0; st < 4; ++st) {
             const Deriv32 d = rhs32(C, cache, edge, px, py, pz, dx, dy, dz, skx, sky, skz);
             const float w = (st == 0 || st == 3) ? 1.0f : 2.0f;
