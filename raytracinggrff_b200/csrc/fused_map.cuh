@@ -25,6 +25,7 @@ namespace rtgrff {
 struct FreqDev {
     double nu, omega0, dt;
     int64_t n_steps, stride;
+    int out_row;          // row of this frequency in the caller's tb / vi arrays
     StepConst K;
     FreqC fq;
 };
@@ -39,7 +40,6 @@ struct MapArgs {
     const double *x_start, *y_start, *z_start, *kvec;
     const int *ray_order;                // thread t handles ray ray_order[t] (nullptr: t); see rtgrff.h
     int n_freq;                          // <= kMaxFreqPerLaunch
-    int freq_base;                       // index of freqs[0] in the caller's frequency list (output row)
     FreqDev freqs[kMaxFreqPerLaunch];
     double perturb_ratio, area;
     float r_sun_cm, fill_ne, fill_te, fill_b;
@@ -235,8 +235,8 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_MINB) render_map_kernel(const Map
         double tb, vi, IL, IR;
         tr.result(IL, IR);
         tb_vi(IL, IR, fp.nu, a.area, tb, vi);
-        a.tb[(size_t)(a.freq_base + fi) * a.n_rays + ray] = tb;
-        a.vi[(size_t)(a.freq_base + fi) * a.n_rays + ray] = vi;
+        a.tb[(size_t)fp.out_row * a.n_rays + ray] = tb;
+        a.vi[(size_t)fp.out_row * a.n_rays + ray] = vi;
     }
     if (a.active_steps) {
         // a ray moves on steps [0, death): the counters follow from where it froze

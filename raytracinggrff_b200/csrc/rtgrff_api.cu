@@ -2,6 +2,7 @@
 // the kernels live in the .cuh files next to this one.
 #include <stdarg.h>
 
+#include <algorithm>
 #include <mutex>
 #include <new>
 #include <vector>
@@ -690,6 +691,7 @@ int rtgrff_render_map(rtgrff_ctx *c, int64_t n_rays, const double *x_start, cons
         fd[f].dt = freqs[f].dt;
         fd[f].n_steps = freqs[f].n_steps;
         fd[f].stride = freqs[f].record_stride;
+        fd[f].out_row = f;
         fd[f].K = make_step_const(rc, freqs[f].dt, perturb_ratio);
         fd[f].fq = make_freq(freqs[f].freq_hz);
         nominal += freqs[f].n_steps * n_rays;
@@ -741,9 +743,16 @@ int rtgrff_render_map(rtgrff_ctx *c, int64_t n_rays, const double *x_start, cons
         if (!(max_stage_offset_cells(freqs[f].dt, trace_cs ? perturb_ratio : 0.0, c->wgeom.idx, c->wgeom.idy,
                                      c->wgeom.idz) < kMaxStageOffsetCells))
             mode = MODE_F64;
+    // Longest frequencies first: blocks are dispatched in grid order, and a launch that ends on its
+    // most expensive blocks (15 000 steps with a record at every step) idles most of the chip in its tail.
+    std::stable_sort(fd.begin(), fd.end(), [&](const FreqDev &x, const FreqDev &y) {
+        auto cost = [&](const FreqDev &q) {
+            return (double)q.n_steps * (1.0 + ((trace_cs ? 2.0 : 0.0) + 1.0) / (double)q.stride);
+        };
+        return cost(x) > cost(y);
+    });
     // the per-frequency constants travel in the kernel parameters: kMaxFreqPerLaunch frequencies per launch
     for (int f0 = 0; f0 < n_freq; f0 += kMaxFreqPerLaunch) {
-    a.freq_base = f0;
     a.n_freq = n_freq - f0 < kMaxFreqPerLaunch ? n_freq - f0 : kMaxFreqPerLaunch;
     for (int f = 0; f < a.n_freq; ++f) a.freqs[f] = fd[f0 + f];
     const dim3 grid(blocks_for(n_rays, RT_BLOCK), (unsigned int)a.n_freq);
