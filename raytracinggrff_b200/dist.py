@@ -5,7 +5,9 @@ all-gather of the image slabs at the end.
 This is the reference's only parallel strategy — data parallel over contiguous ray chunks with a
 concatenate at the end (script/resample_with_ray_tracing.py:42-61, :333-352) — with two changes:
 rows are interleaved instead of contiguous because disk-centre rays live much longer than limb
-rays, and the exchange is a collective instead of pickles over pipes.  Rays never
+rays — in groups of 8 adjacent rows, the height of the pixel tile a warp walks
+(RaySession.render_map), so that a warp's 32 rays stay neighbours in the real image — and the
+exchange is a collective instead of pickles over pipes.  Rays never
 interact, so there is no data-path collective during integration.
 """
 from __future__ import annotations
@@ -13,13 +15,23 @@ from __future__ import annotations
 import numpy as np
 
 
+ROW_GROUP = 8      # = the tile height of RaySession.render_map(tile=(4, 8))
+
+
+def row_group(n_rows: int, world_size: int) -> int:
+    """Rows dealt together: 8 when every rank still gets at least 8 groups (load balance), else 1."""
+    return ROW_GROUP if n_rows >= 8 * ROW_GROUP * world_size else 1
+
+
 def rows_of_rank(n_rows: int, world_size: int, rank: int) -> np.ndarray:
-    """Image rows owned by `rank`: rank, rank+W, rank+2W, ..."""
-    return np.arange(rank, n_rows, world_size)
+    """Image rows owned by `rank`: groups of row_group() adjacent rows dealt round-robin
+    (group g -> rank g mod W); with groups of one row that is rank, rank+W, rank+2W, ..."""
+    g = np.arange(n_rows) // row_group(n_rows, world_size)
+    return np.flatnonzero(g % world_size == rank)
 
 
 def max_rows_per_rank(n_rows: int, world_size: int) -> int:
-    return (n_rows + world_size - 1) // world_size
+    return max(len(rows_of_rank(n_rows, world_size, r)) for r in range(world_size))
 
 
 def shard_rays(N_pix_x: int, N_pix_y: int, world_size: int, rank: int):
@@ -46,6 +58,6 @@ def gather_rows(local, n_rows: int, group=None):
     buf = buf.view((world,) + tuple(local.shape))
     full = torch.empty(tuple(local.shape[:-2]) + (n_rows, local.shape[-1]), dtype=local.dtype, device=local.device)
     for r in range(world):
-        n_r = len(range(r, n_rows, world))
-        full[..., r::world, :] = buf[r][..., :n_r, :]
+        rows = torch.from_numpy(rows_of_rank(n_rows, world, r)).to(local.device)
+        full[..., rows, :] = buf[r][..., :len(rows), :]
     return full

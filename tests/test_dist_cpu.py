@@ -34,7 +34,7 @@ def _worker(rank, world, port, n_rows, n_x, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n_rows", [(2, 8), (2, 7), (3, 10)])
+@pytest.mark.parametrize("world,n_rows", [(2, 8), (2, 7), (3, 10), (2, 150), (3, 200)])
 def test_interleaved_rows_gather(world, n_rows):
     n_x = 5
     ctx = mp.get_context("spawn")
@@ -59,3 +59,11 @@ def test_shard_covers_every_ray_once():
         assert np.array_equal(np.sort(seen), np.arange(16 * 37))
         sizes = [len(rdist.rows_of_rank(37, world, r)) for r in range(world)]
         assert max(sizes) - min(sizes) <= 1 and max(sizes) == rdist.max_rows_per_rank(37, world)
+    # large images: rows go out in groups of 8 adjacent rows (the tile height), still every row exactly once,
+    # shares within one group of each other
+    for world, n_rows in ((2, 512), (8, 2048), (8, 4096), (3, 1000)):
+        assert rdist.row_group(n_rows, world) == 8
+        rows = [rdist.rows_of_rank(n_rows, world, r) for r in range(world)]
+        assert np.array_equal(np.sort(np.concatenate(rows)), np.arange(n_rows))
+        assert max(map(len, rows)) - min(map(len, rows)) <= 8
+        assert np.array_equal(rows[1][:8], np.arange(8, 16))
