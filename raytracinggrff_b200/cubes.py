@@ -47,6 +47,17 @@ def cart_to_sph(x, y, z, phi0_offset=0.0):
     return r, colat, lon
 
 
+def load_mas_var_filtered(model, var_name):
+    """``raytracingGRFF/build_rays.py:48-66`` reads ``<var>NNN.hdf`` files of a psipy ``MASOutput`` — file I/O
+    that is out of scope here (psipy is not available).  For the in-memory models of this package
+    (``name -> SphericalVariable``) it returns the variable, so code written against the reference's
+    import keeps working on them; anything else raises."""
+    if isinstance(model, dict) and var_name in model and isinstance(model[var_name], SphericalVariable):
+        return model[var_name]
+    raise RuntimeError("load_mas_var_filtered: reading MAS HDF files needs psipy (out of scope); pass a model "
+                       "{name: SphericalVariable} (cubes.load_spherical_model) instead")
+
+
 def _resample(ctx, slot, var, x_grid, y_grid, z_grid, phi0_offset, fill_nan, r_min, fetch):
     geom = _lib.grid_geom(x_grid, y_grid, z_grid)
     data = f32(var.data)
