@@ -197,7 +197,7 @@ constexpr double kMaxStageOffsetCells = 8.0;
 __host__ __device__ inline double max_stage_offset_cells(double dt, double perturb_ratio, double idx, double idy, double idz)
 {
     const double i = fmax(idx, fmax(idy, idz));
-    return (1.0 + fabs(perturb_ratio)) * dt * kC_R * i;
+    return (1.0 + fabs(perturb_ratio)) * fabs(dt) * kC_R * i;     // dt < 0 traces backwards
 }
 
 // Per-launch float constants derived from dt and the grid (uniform across the grid).

@@ -567,3 +567,20 @@ def test_rays_through_the_density_discontinuity(oracle, session):
     assert bad.mean() < 0.03, f"{bad.sum()} of {bad.size} rays deviate"
     assert np.all(closest[bad] < 1.0), "only rays that dive below the surface may deviate"
     assert np.median(dev) < 5e-7 and np.quantile(dev, 0.95) < 2e-6
+
+
+def test_trace_backwards_in_time(oracle, session):
+    """dt < 0 (the reference takes any float dt): parity with the oracle, and a forward trace followed
+    by a backward trace from its end point (k reversed in time = same k, negative dt) retraces the path."""
+    c = synthetic.corona_cube(48, 3.0)
+    session.set_omega_cube(c["omega_pe"], c["x_grid"], c["y_grid"], c["z_grid"])
+    rng = np.random.default_rng(4)
+    m = 32
+    xs, ys, zs = rng.uniform(-1.0, 1.0, m), rng.uniform(-1.0, 1.0, m), rng.uniform(1.6, 2.4, m)
+    kv = np.column_stack([rng.normal(scale=0.3, size=m), rng.normal(scale=0.3, size=m), np.ones(m)])
+    kv /= np.linalg.norm(kv, axis=1, keepdims=True)
+    r, s, _ = session.trace(90e6, xs, ys, zs, kv, -5e-3, 300, 5, True, 2.0)
+    r_ref, cs_ref = oracle.ray_trace(c["omega_pe"], c["x_grid"], c["y_grid"], c["z_grid"], 90e6, xs, ys, zs, kv, -5e-3,
+                                     300, 5, True, perturb_ratio=2)
+    _cmp_paths(r, s, r_ref, np.array(cs_ref), lo=np.full(3, -3.0), hi=np.full(3, 3.0), step_len=1.01 * 5e-3 * 0.43075)
+    assert np.nanmax(np.abs(r[-1] - np.column_stack([xs, ys, zs]))) > 0.1      # the rays did move
