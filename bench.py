@@ -192,12 +192,13 @@ def config_dict(w, args):
         "workload": f"BASELINE {w['name']}: {w['n_pix_x']}x{w['n_pix_y']} px, {w['grid_n']}^3 cube, {w['n_freq']} freqs "
                     f"{w['f0'] / 1e6:g}-{w['f1'] / 1e6:g} MHz, GR+FF, cross-sections on, fused trace+sample+transfer",
         "per_freq": [[p["freq_hz"], p["dt"], p["n_steps"], p["record_stride"]] for p in w["freq_params"]],
-        "sharding": "rows interleaved over ranks, cube replicated, NCCL all-gather of the image",
+        "sharding": "rows interleaved over ranks in groups of 8, cube replicated, NCCL all-gather of the image",
         "thread_order": "4x8-pixel tiles per warp (ray_order), results in row-major ray order",
-        "l2": f"cubes (3 x {16 * w['grid_n'] ** 3 / 1e6:.0f} MB float4) exceed the 126 MB L2; no flush between steps",
+        "l2": f"cubes (3 x {16 * w['grid_n'] ** 3 / 1e6:.0f} MB float4 + {128 * w['grid_n'] ** 3 / 1e6:.0f} MB cell-major polynomial "
+              "cube) exceed the 126 MB L2; no flush between steps",
         "cubes": "built on the GPU from a spherical (phi,lat,r) model" if (w["name"] == "config5" or args.spherical)
                  else "analytic corona, uploaded from pinned host memory",
-        "precision": "FP64 ray state and transfer, FP32 cube storage and cell-relative RHS",
+        "precision": "FP64 ray state and transfer, FP32 cube storage and cell-relative RHS, FP32 angle to B",
         "cross_sections": "pencil rays traced on recorded steps only (the reference computes S at every step but "
                           "outputs only recorded steps, build_rays.py:241-244); RTGRFF_CS_EVERY_STEP=1 restores it",
     }
