@@ -584,3 +584,27 @@ def test_trace_backwards_in_time(oracle, session):
                                      300, 5, True, perturb_ratio=2)
     _cmp_paths(r, s, r_ref, np.array(cs_ref), lo=np.full(3, -3.0), hi=np.full(3, 3.0), step_len=1.01 * 5e-3 * 0.43075)
     assert np.nanmax(np.abs(r[-1] - np.column_stack([xs, ys, zs]))) > 0.1      # the rays did move
+
+
+def test_render_map_many_frequencies_order_and_chunks(session):
+    """More frequencies than fit one launch (16 per launch, dispatched longest first): every row of the
+    result must equal the single-frequency render of that frequency, bit for bit."""
+    c = synthetic.corona_cube(48, 3.0, active_region=True)
+    session.set_omega_cube(c["omega_pe"], c["x_grid"], c["y_grid"], c["z_grid"])
+    session.set_field_cubes(c["x_grid"], c["y_grid"], c["z_grid"], c["ne"], c["te"], c["b"], c["bx"], c["by"], c["bz"])
+    xs, ys, zs, kv = synthetic.ray_launch_geometry(6, 1.2, 3.0)
+    area = (2 * 1.2 / 6 * 6.957e10) ** 2
+    rng = np.random.default_rng(8)
+    freqs = rng.permutation(np.geomspace(60e6, 900e6, 19))          # unsorted on purpose
+    fps = [dict(freq_hz=float(f), dt=6e-3 * (100e6 / f) ** 0.5, n_steps=int(600 + 40 * i), record_stride=1 + i % 4)
+           for i, f in enumerate(freqs)]
+    kw = dict(kvec_in_norm=kv, pixel_area_cm2=area, em_flag=4, use_bvec=True)
+    tb, vi, st = session.render_map(xs, ys, zs, fps, **kw)
+    assert tb.shape == (19, 36) and st["nominal_ray_steps"] == 36 * sum(p["n_steps"] for p in fps)
+    act = 0
+    for i, p in enumerate(fps):
+        tb1, vi1, st1 = session.render_map(xs, ys, zs, [p], **kw)
+        assert np.array_equal(tb[i], tb1[0]) and np.array_equal(vi[i], vi1[0]), i
+        act += st1["active_ray_steps"]
+    assert act == st["active_ray_steps"]
+    assert (tb > 0).any()
