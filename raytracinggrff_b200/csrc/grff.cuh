@@ -221,7 +221,9 @@ __device__ __forceinline__ DiagOp voxel_op(const FreqC &f, const Voxel &v)
             const double ab = a * b, r = 1.0 / (ab * sD);
             inv_sD = r * ab; inv_dX = r * (b * sD); inv_dO = r * (a * sD);
         } else {
-            inv_sD = 1.0 / sD; inv_dX = 1.0 / dX; inv_dO = 1.0 / dO;
+            inv_sD = 1.0 / sD;
+            inv_dX = x_on ? 1.0 / dX : 0.0;
+            inv_dO = o_on ? 1.0 / dO : 0.0;
         }
         if (x_on) {
             const double n2 = 1.0 - vo2 * inv_dX;
@@ -396,10 +398,16 @@ struct SliceArgs {
 
 // Parms[14] > 0 is the S input (script/resample_with_ray_tracing.py:501): the voxel's own source area
 // S_k * area; its source term scales by Parms[14] / area (definition in oracle/oracle_grff.c).
+__device__ __forceinline__ double load_scale(const double *P, double area)
+{
+    const double s = P[14];
+    return s > 0.0 ? s / area : 1.0;
+}
+
 __device__ __forceinline__ Voxel load_voxel(const double *P, double area)
 {
     Voxel v = make_voxel(P[0], P[1], P[2], P[3], P[4], (int)P[6], (int)P[7]);
-    if (P[14] > 0.0) v.scale = P[14] / area;
+    v.scale = load_scale(P, area);
     return v;
 }
 
@@ -431,8 +439,15 @@ __global__ void __launch_bounds__(128) grff_slice_kernel(const SliceArgs a)
             const Voxel v = load_voxel(P + (size_t)k * 15, R[0]);
             if (v.ok) {
                 if (k > 0) {
-                    const Voxel pv = load_voxel(P + (size_t)(k - 1) * 15, R[0]);
-                    if (pv.ok && pv.B > 0.0 && v.B > 0.0) { bt = between_voxels(fq, pv, v); has_bt = true; }
+                    // the previous voxel without its S input; that (one more scattered load) and the event
+                    // list are only needed where something can happen between the two voxels
+                    const double *Pp = P + (size_t)(k - 1) * 15;
+                    Voxel pv = make_voxel(Pp[0], Pp[1], Pp[2], Pp[3], Pp[4], (int)Pp[6], (int)Pp[7]);
+                    if (pv.ok && pv.B > 0.0 && v.B > 0.0 && between_needed(fq, pv, v)) {
+                        pv.scale = load_scale(Pp, R[0]);
+                        bt = between_voxels(fq, pv, v);
+                        has_bt = true;
+                    }
                 }
                 op = voxel_op<false>(fq, v);
             }
