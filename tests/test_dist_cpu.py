@@ -67,3 +67,22 @@ def test_shard_covers_every_ray_once():
         assert np.array_equal(np.sort(np.concatenate(rows)), np.arange(n_rows))
         assert max(map(len, rows)) - min(map(len, rows)) <= 8
         assert np.array_equal(rows[1][:8], np.arange(8, 16))
+
+
+def test_row_sharding_is_a_partition_for_any_size():
+    """Every row exactly once, rank shares within one group of each other, groups of 8 only when every
+    rank still gets at least 8 of them."""
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        world = int(rng.integers(1, 9))
+        n_rows = int(rng.integers(1, 5000))
+        rows = [rdist.rows_of_rank(n_rows, world, r) for r in range(world)]
+        assert np.array_equal(np.sort(np.concatenate(rows)), np.arange(n_rows))
+        g = rdist.row_group(n_rows, world)
+        assert g == (8 if n_rows >= 64 * world else 1)
+        assert max(map(len, rows)) - min(map(len, rows)) <= g
+        assert rdist.max_rows_per_rank(n_rows, world) == max(map(len, rows))
+        for r in range(world):
+            assert np.all(np.diff(rows[r]) > 0)
+            idx, rr = rdist.shard_rays(7, n_rows, world, r)
+            assert np.array_equal(rr, rows[r]) and idx.size == 7 * len(rows[r])
