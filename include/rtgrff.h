@@ -38,8 +38,15 @@ int rtgrff_device_count(void);
 
 /* One context per GPU.  `stream` is a cudaStream_t passed as void* (NULL = the library creates
  * its own non-blocking stream).  Passing torch's current stream makes torch CUDA events see the
- * library's kernels. */
+ * library's kernels.  Every entry point switches to the context's device for the duration of the
+ * call and restores the caller's current device before it returns. */
 int rtgrff_ctx_create(int device, void *stream, rtgrff_ctx **out);
+/* Same, but `stream` is always the caller's stream — including 0, the legacy default stream (which
+ * is torch's default stream): all work of the context is then ordered with the caller's own work on
+ * that stream, as buffers shared with the caller (out_on_device, on_device) require. */
+int rtgrff_ctx_create_on_stream(int device, void *stream, rtgrff_ctx **out);
+/* The calling thread's current CUDA device (module-level Python drop-ins default to it); <0 on error. */
+int rtgrff_current_device(void);
 int rtgrff_ctx_destroy(rtgrff_ctx *ctx);
 int rtgrff_ctx_synchronize(rtgrff_ctx *ctx);
 /* Kernel launches issued by this context since creation (for bench.py's gpu_launches). */
@@ -168,6 +175,28 @@ int rtgrff_get_mw_slice(rtgrff_ctx *ctx, const int32_t *Lparms_M, const double *
                         const double *Parms_M, const double *T_arr, const double *DEM_arr,
                         const double *DDM_arr, double *RL_M, int32_t *status);
 
+/* The same call on DEVICE arrays — what the reference actually hands fastGRFF: CuPy Rparms_M / Parms_M /
+ * RL_M with RL_M written in place on the device (script/resample_with_ray_tracing.py:428-446).
+ * Lparms_M is host memory (6 integers); status_dev is a device int32 (Npix) or NULL. */
+int rtgrff_get_mw_slice_device(rtgrff_ctx *ctx, const int32_t *Lparms_M, const double *Rparms_M_dev,
+                               const double *Parms_M_dev, double *RL_M_dev, int32_t *status_dev);
+
+/* Device memory on the context's GPU for callers without a CUDA binding of their own (image slabs for
+ * rtgrff_render_map(out_on_device) + rtgrff_gather_image, staging of the *_device variants). */
+int rtgrff_device_alloc(rtgrff_ctx *ctx, void **out, size_t bytes);
+int rtgrff_device_free(rtgrff_ctx *ctx, void *ptr);
+
+/* Plain copy on the context's stream, synchronous: kind 0 host->device, 1 device->host, 2 device->device.
+ * Lets a host language without its own CUDA binding stage the device-array variants above. */
+int rtgrff_memcpy(rtgrff_ctx *ctx, void *dst, const void *src, size_t bytes, int kind);
+
+/* Copies of the device cubes back to the host (any pointer may be NULL): omega_pe float64 exactly as it
+ * was differenced (available after rtgrff_compose_cubes / a host rtgrff_set_omega_cube until the next
+ * cube upload), n_e, T, |B| and the B vector as stored (float32), each (nx,ny,nz) C-order.  For parity
+ * checks of cubes that were built on the device (rtgrff_compose_cubes) against a CPU implementation. */
+int rtgrff_export_cubes(rtgrff_ctx *ctx, double *omega_pe, float *ne, float *te, float *b, float *bx,
+                        float *by, float *bz);
+
 /*
  * GRFF + T_b conversion on the samples left on the device by rtgrff_sample_traced(): the
  * per-pixel loop of script/resample_with_ray_tracing.py:467-530 (valid filter, Parms packing with
@@ -218,6 +247,35 @@ int rtgrff_render_map(rtgrff_ctx *ctx, int64_t n_rays, const double *x_start, co
                       double pixel_area_cm2, double r_sun_cm, int em_flag, int s_max, int use_bvec,
                       int voxel_order, int s_mode, int s_input_on, double *tb, double *vi,
                       int out_on_device, int64_t *stats);
+
+/*
+ * Multi-GPU (one process per GPU, the cube replicated on each).  Rays are independent, so the only exchange
+ * is the gather of the image at the end; this replaces the reference's ProcessPoolExecutor ray chunks and
+ * their concatenate (script/resample_with_ray_tracing.py:42-61, :333-352, the `--workers` switch).
+ *
+ * rtgrff_shard_rows: the image rows rank `rank` of `world_size` renders — rows are dealt round-robin in
+ * groups of 8 adjacent rows (one by one for small images) because disk-centre rays run much longer than
+ * limb rays.  rows: int32 (n_rows) buffer receiving the row indices (may be NULL), n_local their number,
+ * max_rows the largest share of any rank (the slab height of rtgrff_gather_image).  Host only, no GPU needed.
+ */
+int rtgrff_shard_rows(int n_rows, int world_size, int rank, int32_t *rows, int *n_local, int *max_rows);
+
+/* NCCL communicator over the contexts of all ranks (NCCL is loaded at run time: libnccl.so.2).  Rank 0 calls
+ * rtgrff_comm_unique_id and hands the 128 bytes to the other ranks by whatever channel the host has (a file,
+ * MPI, torch.distributed ...); then every rank calls rtgrff_comm_init_rank (collective).  world_size 1 needs no id. */
+int rtgrff_comm_unique_id(char id[128]);
+int rtgrff_comm_init_rank(rtgrff_ctx *ctx, int world_size, int rank, const char id[128]);
+int rtgrff_comm_destroy(rtgrff_ctx *ctx);
+
+/*
+ * Gather the ranks' image slabs on `root` and put every row at its place (collective over the communicator;
+ * a single-rank context just reorders).  slab: device float64 (n_planes, max_rows, n_cols), the rank's rows in
+ * the order rtgrff_shard_rows lists them, padding after — what rtgrff_render_map writes with out_on_device when
+ * its rays are the rank's rows (planes = [tb | vi] x frequency).  image (root only): float64 (n_planes, n_rows,
+ * n_cols), a device pointer when image_on_device, else host memory (page-locked memory is written by DMA directly).
+ */
+int rtgrff_gather_image(rtgrff_ctx *ctx, const double *slab, int n_planes, int n_rows, int n_cols, int root,
+                        double *image, int image_on_device);
 
 /*
  * Gaussian beam on the image plane: scipy.ndimage.gaussian_filter(map, sigma) as the workflow

@@ -72,7 +72,17 @@ def _lib():
         _LIB.oracle_get_mw.restype = ctypes.c_int
         _LIB.oracle_get_mw_slice.argtypes = [ip, dp, dp, dp, dp, dp, dp, ip]
         _LIB.oracle_get_mw_slice.restype = ctypes.c_int
+        _LIB.oracle_set_num_threads.argtypes = [ctypes.c_int]
+        _LIB.oracle_set_num_threads.restype = None
     return _LIB
+
+
+def set_num_threads(n=None):
+    """OpenMP threads of every oracle stage (default: all host cores, whatever OMP_NUM_THREADS says —
+    torchrun sets it to 1 for its workers)."""
+    n = int(n or os.cpu_count() or 1)
+    _lib().oracle_set_num_threads(n)
+    return n
 
 
 def _p(a, ct):
@@ -272,6 +282,87 @@ def emission_from_samples(sampled, N_pix, X_fov, freq0, Nfreq=1, freq_log_step=0
             emission_polVI_cube[i, j, f] = pol
     emission_cube = np.nan_to_num(emission_cube, nan=0.0, posinf=0.0, neginf=0.0)
     return emission_cube, emission_polVI_cube, frequencies_Hz
+
+
+def chain_bvec(cube, freq_hz, dt, n_steps, record_stride, xs, ys, zs, area, em_flag=4, s_max=30, perturb_ratio=2,
+               n_threads=0, ray_chunk=128, return_paths=False):
+    """The reference chain for a GR+FF map with the angle to B taken along the ray — the physics the fused
+    kernel is benchmarked on (BASELINE configs 4 and 5), restated with the reference's own stages:
+      ray_trace (build_rays.py:128-248, cross-sections on)
+      -> sample_model_with_rays twice, (ne, te, b) and (bx, by, bz)     (gpu_raytrace.py:632-651)
+      -> Parms per pixel as script/resample_with_ray_tracing.py:472-501, except Parms[3] = |B vector| and
+         Parms[4] = theta = acos(-B.d / |B||d|), d the step from the previous valid float32 sample (the ray
+         start for the first) to this one; Parms[6] = em_flag, Parms[7] = s_max
+      -> GET_MW (batched over pixels) -> T_b, V/I (:513-520).
+    The reference itself fixes theta = 90 deg (:495); theta from B is this repo's extension.
+    cube: dict with x_grid, y_grid, z_grid, omega_pe, ne, te, b, bx, by, bz.  Returns (tb, vi) each (n_rays,)
+    [and r_record, s_record when return_paths]."""
+    kv = np.tile([[0.0, 0.0, -1.0]], (len(xs), 1))
+    ray_start = np.column_stack([xs, ys, zs])
+    g3 = (cube["x_grid"], cube["y_grid"], cube["z_grid"])
+    r, cs = ray_trace(cube["omega_pe"], *g3, freq_hz, xs, ys, zs, kv, dt, n_steps, record_stride, True,
+                      perturb_ratio=perturb_ratio, n_threads=n_threads)
+    s_rec = np.array(cs)
+    smp = sample_model_with_rays_cpu(*g3, cube["ne"], cube["te"], cube["b"], r, s_rec, ray_start, R_SUN_CM)
+    bv = sample_model_with_rays_cpu(*g3, cube["bx"], cube["by"], cube["bz"], r, s_rec, ray_start, R_SUN_CM,
+                                    fill_ne=0.0, fill_te=0.0, fill_b=0.0)
+    tb, vi = emission_bvec_from_samples(smp, bv, r, ray_start, area, freq_hz, em_flag, s_max, ray_chunk)
+    if return_paths:
+        return tb, vi, r, s_rec
+    return tb, vi
+
+
+def emission_bvec_from_samples(smp, bv, r_record, ray_start, area, freq_hz, em_flag=4, s_max=30, ray_chunk=128):
+    """Parms packing with theta from the sampled B vector + batched GET_MW + T_b conversion (see chain_bvec)."""
+    n_rec, n_rays = smp["ne"].shape
+    tb = np.zeros(n_rays)
+    vi = np.zeros(n_rays)
+    conv = (SFU2CGS * C_CGS * C_CGS / (2.0 * KB_CGS * freq_hz * freq_hz) / area) * (AU_CM * AU_CM)
+    for c0 in range(0, n_rays, ray_chunk):
+        sl = slice(c0, min(n_rays, c0 + ray_chunk))
+        nr = sl.stop - sl.start
+        valid = smp["valid_mask"][:, sl]
+        pos = r_record[:, sl].astype(np.float32).astype(np.float64)
+        start = np.asarray(ray_start)[sl].astype(np.float32).astype(np.float64)
+        # previous valid sample of every record (the ray start before the first one)
+        idx = np.where(valid, np.arange(n_rec)[:, None], -1)
+        last = np.maximum.accumulate(idx, axis=0)
+        prev = np.vstack([np.full((1, nr), -1, dtype=last.dtype), last[:-1]])
+        prev_pos = np.take_along_axis(pos, np.broadcast_to(np.maximum(prev, 0)[:, :, None], pos.shape), axis=0)
+        prev_pos = np.where(prev[:, :, None] >= 0, prev_pos, start[None])
+        d = pos - prev_pos
+        B = np.stack([bv["ne"][:, sl], bv["te"][:, sl], bv["b"][:, sl]], axis=2).astype(np.float64)
+        b2 = (B * B).sum(2)
+        dn2 = (d * d).sum(2)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            cth = np.clip(-(B * d).sum(2) / np.sqrt(b2 * dn2), -1.0, 1.0)
+        cth = np.where((b2 > 0) & (dn2 > 0), cth, 6.123233995736766e-17)
+        theta = np.degrees(np.arccos(cth))
+        ne, te, ds = smp["ne"][:, sl], smp["te"][:, sl], smp["ds"][:, sl]
+        bmag = np.sqrt(b2)
+        keep_src = valid & np.isfinite(ne) & np.isfinite(te) & np.isfinite(bmag)
+        order = np.argsort(~keep_src, axis=0, kind="stable")
+        cnt = keep_src.sum(axis=0)
+        nz = int(cnt.max()) if nr else 0
+        if nz == 0:
+            continue
+        keep = np.arange(nz)[:, None] < cnt[None, :]
+        P = np.zeros((15, nz, nr), dtype=np.float64, order="F")
+        for m, a in ((0, ds), (1, te), (2, ne), (3, bmag), (4, theta)):
+            P[m] = np.where(keep, np.take_along_axis(a.astype(np.float64), order, axis=0)[:nz], 0.0)
+        P[6] = em_flag
+        P[7] = s_max
+        L = np.array([nr, nz, 1, 1, 0, 0], dtype=np.int32)
+        R = np.zeros((3, nr), order="F")
+        R[0], R[1], R[2] = area, freq_hz, 0.0
+        RL = np.zeros((7, 1, nr), order="F")
+        status = get_mw_slice(L, R, P, None, None, None, RL)
+        ok = (status == 0) & (cnt > 0)
+        inten = RL[5, 0] + RL[6, 0]
+        tb[sl] = np.where(ok, inten * conv, 0.0)
+        vi[sl] = np.where(ok, (RL[5, 0] - RL[6, 0]) / (inten + 1e-30), 0.0)
+    tb = np.nan_to_num(tb, nan=0.0, posinf=0.0, neginf=0.0)
+    return tb, vi
 
 
 def emission_from_los(Ne_LOS, Te_LOS, B_LOS, ds_LOS, pixel_area_cm2, freq0, Nfreq, freq_log_step):

@@ -205,6 +205,17 @@ static inline double cross_section_ratio(const cube_t *c, const double s0[6], co
  *  move (bookkeeping for the benchmark, not part of the reference).
  * Returns 0, or -1 on allocation failure.
  */
+/* Thread count of every OpenMP region of the oracle (ray_trace, sampler, get_mw_slice): a launcher such as
+ * torchrun exports OMP_NUM_THREADS=1 to its workers, which would serialise the CPU baseline. */
+void oracle_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int oracle_ray_trace(const double *omega_pe, const double *xg, const double *yg, const double *zg,
                      int nx, int ny, int nz, double freq_hz,
                      const double *x_start, const double *y_start, const double *z_start,

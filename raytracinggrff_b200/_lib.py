@@ -36,6 +36,9 @@ EXPORTS = (
     "rtgrff_resample_spherical", "rtgrff_compose_cubes", "rtgrff_sample_spherical_los",
     "rtgrff_trace", "rtgrff_sample", "rtgrff_sample_traced", "PyGET_MW", "rtgrff_get_mw_slice",
     "rtgrff_emission_traced", "rtgrff_render_map", "rtgrff_gaussian_beam", "rtgrff_patch_nan",
+    "rtgrff_ctx_create_on_stream", "rtgrff_current_device", "rtgrff_get_mw_slice_device", "rtgrff_memcpy",
+    "rtgrff_export_cubes", "rtgrff_shard_rows", "rtgrff_comm_unique_id", "rtgrff_comm_init_rank",
+    "rtgrff_comm_destroy", "rtgrff_gather_image", "rtgrff_device_alloc", "rtgrff_device_free",
 )
 
 
@@ -62,6 +65,18 @@ def load():
     lib.rtgrff_last_error.restype = c_char_p
     lib.rtgrff_device_count.restype = c_int
     lib.rtgrff_ctx_create.argtypes = [c_int, c_void_p, POINTER(c_void_p)]
+    lib.rtgrff_ctx_create_on_stream.argtypes = [c_int, c_void_p, POINTER(c_void_p)]
+    lib.rtgrff_current_device.restype = c_int
+    lib.rtgrff_get_mw_slice_device.argtypes = [c_void_p, ip, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.rtgrff_device_alloc.argtypes = [c_void_p, POINTER(c_void_p), ctypes.c_size_t]
+    lib.rtgrff_device_free.argtypes = [c_void_p, c_void_p]
+    lib.rtgrff_memcpy.argtypes = [c_void_p, c_void_p, c_void_p, ctypes.c_size_t, c_int]
+    lib.rtgrff_export_cubes.argtypes = [c_void_p, dp, fp, fp, fp, fp, fp, fp]
+    lib.rtgrff_shard_rows.argtypes = [c_int, c_int, c_int, ip, POINTER(c_int), POINTER(c_int)]
+    lib.rtgrff_comm_unique_id.argtypes = [ctypes.c_char_p]
+    lib.rtgrff_comm_init_rank.argtypes = [c_void_p, c_int, c_int, ctypes.c_char_p]
+    lib.rtgrff_comm_destroy.argtypes = [c_void_p]
+    lib.rtgrff_gather_image.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int]
     lib.rtgrff_ctx_destroy.argtypes = [c_void_p]
     lib.rtgrff_ctx_synchronize.argtypes = [c_void_p]
     lib.rtgrff_ctx_launch_count.argtypes = [c_void_p]
@@ -114,6 +129,27 @@ def ptr(a, ctype):
     return None if a is None else a.ctypes.data_as(POINTER(ctype))
 
 
+def cuda_array(a):
+    """(device pointer, shape, typestr, strides) of an object exposing ``__cuda_array_interface__`` (CuPy
+    arrays, torch CUDA tensors, numba device arrays), else None."""
+    cai = getattr(a, "__cuda_array_interface__", None)
+    if cai is None:
+        return None
+    return int(cai["data"][0]), tuple(cai["shape"]), cai["typestr"], cai.get("strides")
+
+
+def is_f_contiguous(shape, strides, itemsize):
+    """Fortran-contiguity of a __cuda_array_interface__ array (strides None = C-contiguous)."""
+    if strides is None:
+        return sum(1 for n in shape if n > 1) <= 1
+    expect = itemsize
+    for n, st in zip(shape, strides):
+        if n > 1 and st != expect:
+            return False
+        expect *= n
+    return True
+
+
 def f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
@@ -149,21 +185,37 @@ def grid_geom(x_grid, y_grid, z_grid):
     return out
 
 
-class Context:
-    """One GPU context (rtgrff_ctx).  `stream` is an int cudaStream_t handle (e.g.
-    ``torch.cuda.current_stream().cuda_stream``) or None for a library-owned stream."""
+def current_device():
+    """The calling thread's current CUDA device (what torch.cuda.set_device chose)."""
+    d = load().rtgrff_current_device()
+    if d < 0:
+        raise RuntimeError(load().rtgrff_last_error().decode(errors="replace"))
+    return d
 
-    def __init__(self, device=0, stream=None):
+
+class Context:
+    """One GPU context (rtgrff_ctx).  `stream` is an int cudaStream_t handle — e.g.
+    ``torch.cuda.current_stream().cuda_stream``, where 0 is the legacy default stream torch uses by
+    default and is honoured as such — or None for a library-owned stream.  `device` None = the
+    calling thread's current device."""
+
+    def __init__(self, device=None, stream=None):
         lib = load()
         n = lib.rtgrff_device_count()
         if n <= 0:
             raise RuntimeError("No CUDA device is available to raytracinggrff_b200 "
                                f"({lib.rtgrff_last_error().decode(errors='replace') or 'device count 0'}); "
                                "this package has no CPU path.")
+        if device is None:
+            device = current_device()
         h = c_void_p()
-        check(lib.rtgrff_ctx_create(int(device), c_void_p(stream) if stream else None, ctypes.byref(h)))
+        if stream is None:
+            check(lib.rtgrff_ctx_create(int(device), None, ctypes.byref(h)))
+        else:
+            check(lib.rtgrff_ctx_create_on_stream(int(device), c_void_p(int(stream)), ctypes.byref(h)))
         self._h = h
         self.device = int(device)
+        self.stream = stream
         self._lib = lib
 
     def close(self):
@@ -204,8 +256,11 @@ class Context:
 _default_ctx = {}
 
 
-def default_context(device=0):
-    """Process-wide context per device, used by the module-level drop-in functions."""
+def default_context(device=None):
+    """Process-wide context per device, used by the module-level drop-in functions; None = the
+    calling thread's current device (a rank working on cuda:k stays on cuda:k)."""
+    if device is None:
+        device = current_device()
     ctx = _default_ctx.get(device)
     if ctx is None or not ctx._h:
         ctx = _default_ctx[device] = Context(device)

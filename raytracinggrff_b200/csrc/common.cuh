@@ -83,6 +83,12 @@ struct rtgrff_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    // second stream + events + pinned bounce buffers of the chunked host<->device pipelines
+    // (rtgrff_sample, rtgrff_get_mw_slice): host pack / H2D / kernel / D2H / host unpack overlap
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t chunk_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // in[2], kernel[2], out[2]
+    void *pinned[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t pinned_cap[4] = {0, 0, 0, 0};
     int64_t launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // bracket the dominant kernel of the last call
     bool ev_valid = false;
@@ -114,6 +120,13 @@ struct rtgrff_ctx {
     bool slot_set[5] = {false, false, false, false, false};
     int slot_nx = 0, slot_ny = 0, slot_nz = 0;
     double slot_geom[12] = {0};
+    double slot_geoms[5][12] = {{0}};   // geometry each slot was resampled on (compose checks they agree)
+    bool stage_has_omega = false;    // `stage` still holds the float64 omega_pe of the last compose (rtgrff_export_cubes)
+
+    // multi-GPU image gather (rtgrff_comm_*): an ncclComm_t behind a void*, NCCL loaded at run time
+    void *comm = nullptr;
+    int comm_rank = 0, comm_size = 1;
+    rtgrff::DevBuf gather_buf, image_buf;
     rtgrff::DevBuf slot_grids;       // x, y, z node coordinates of the slots' cube
 
     // scratch

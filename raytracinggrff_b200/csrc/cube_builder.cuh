@@ -46,6 +46,10 @@ __device__ __forceinline__ double sample_spherical(const SphMesh &m, double lon,
     // padded phi axis: node -1 = phi[np-1] - 2 pi, node np = phi[0] + 2 pi
     int ip0, ip1;
     double p0, p1;
+    // outside the padded axis psipy's interpolator raises and the reference turns the point into NaN
+    // (build_rays.py:109-117): reachable with a phi0 offset beyond about +180 deg, since cart_to_sph
+    // only wraps negative longitudes
+    if (lon < m.phi[m.np - 1] - two_pi || lon > m.phi[0] + two_pi) return nan("");
     if (lon < m.phi[0]) {
         ip0 = m.np - 1; ip1 = 0; p0 = m.phi[m.np - 1] - two_pi; p1 = m.phi[0];
     } else if (lon >= m.phi[m.np - 1]) {

@@ -229,7 +229,9 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_MINB) render_map_kernel(const Map
                 if (!alive) tail_done = true;
             }
         }
-        if (!__any_sync(0xffffffffu, alive)) break;
+        // a frozen ray still owes its first post-freeze record (with the cross-sections off its S is 1 and the
+        // record counts, exactly as in trace -> sample -> emission): leave only when every lane has handed it over
+        if (!__any_sync(0xffffffffu, alive || !tail_done)) break;
     }
     if (has_ray) {
         double tb, vi, IL, IR;

@@ -252,6 +252,8 @@ struct SampleArgs {
     float r_sun_cm, fill_ne, fill_te, fill_b;
     float *ne, *te, *b, *ds, *s_out;
     uint8_t *valid;
+    int64_t q_begin, q_end;  // the samples [q_begin, q_end) of the (rec, ray) array this launch works on
+                             // (q_end = 0: all) — the chunks of the pipelined host path
 };
 
 __device__ __forceinline__ void load_sample(const SampleArgs &a, int64_t rec, int64_t ray, float &x, float &y,
@@ -274,8 +276,8 @@ __device__ __forceinline__ void load_sample(const SampleArgs &a, int64_t rec, in
 // (usually one step), which keeps the kernel fully parallel over samples.
 __global__ void __launch_bounds__(256) sample_paths_kernel(const SampleArgs a)
 {
-    const int64_t total = a.n_rec * a.n_rays;
-    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total;
+    const int64_t total = a.q_end > 0 ? a.q_end : a.n_rec * a.n_rays;
+    for (int64_t q = a.q_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total;
          q += (int64_t)gridDim.x * blockDim.x) {
         const int64_t rec = q / a.n_rays, ray = q - rec * a.n_rays;
         float x, y, z, s;
@@ -310,6 +312,17 @@ __global__ void interleave3_kernel(const float *__restrict__ a, const float *__r
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n;
          q += (int64_t)gridDim.x * blockDim.x)
         out[q] = make_float4(a[q], b[q], c[q], 0.0f);
+}
+
+// the inverse: one channel-interleaved cube -> three planar arrays (rtgrff_export_cubes)
+__global__ void deinterleave3_kernel(const float4 *__restrict__ in, float *__restrict__ a, float *__restrict__ b,
+                                     float *__restrict__ c, int64_t n)
+{
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n;
+         q += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = in[q];
+        a[q] = v.x; b[q] = v.y; c[q] = v.z;
+    }
 }
 
 }  // namespace rtgrff

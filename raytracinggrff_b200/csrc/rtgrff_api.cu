@@ -5,9 +5,11 @@
 #include <algorithm>
 #include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
+#include "comm.cuh"
 #include "cube_builder.cuh"
 #include "fused_map.cuh"
 #include "grff.cuh"
@@ -79,12 +81,33 @@ static RayCube ray_cube_of(const rtgrff_ctx *c)
     return r;
 }
 
-static int use(rtgrff_ctx *c)
-{
-    if (!c) return fail(RTGRFF_EINVAL, "null context");
-    RT_CUDA(cudaSetDevice(c->device));
-    return RTGRFF_OK;
-}
+// Every entry point runs on the context's device and puts the caller's current device back on
+// exit: a rank that works on cuda:k must not find its thread switched to another GPU after a call.
+struct DeviceGuard {
+    int prev = -1;
+    bool restore = false;
+    ~DeviceGuard()
+    {
+        if (restore) cudaSetDevice(prev);
+    }
+    int enter(const rtgrff_ctx *c)
+    {
+        if (!c) return fail(RTGRFF_EINVAL, "null context");
+        return enter_device(c->device);
+    }
+    int enter_device(int device)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != device) {
+            RT_CUDA(cudaSetDevice(device));
+            restore = prev >= 0;
+        }
+        return RTGRFF_OK;
+    }
+};
+#define RT_USE(c)       \
+    DeviceGuard guard__; \
+    RT_TRY(guard__.enter(c))
 
 static int h2d(rtgrff_ctx *c, DevBuf &b, const void *src, size_t bytes)
 {
@@ -98,6 +121,142 @@ static int d2h(rtgrff_ctx *c, void *dst, const void *src, size_t bytes)
     if (bytes) RT_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
     return RTGRFF_OK;
 }
+
+// ---- chunked host <-> device pipelines -----------------------------------------------------------
+// The reference-facing entry points take pageable host arrays (numpy).  cudaMemcpyAsync on pageable
+// memory is staged by the driver and serialises with everything else (config 1: 0.45 ms of kernel
+// inside 93 ms of copies).  Large calls therefore go through pinned bounce buffers in chunks: the
+// host packs chunk k+1 and unpacks chunk k-1 with a few threads while the DMA engines move chunk k
+// in both directions (H2D on the compute stream, D2H on the copy stream) and the kernel runs on it.
+static int pipeline_enabled()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("RTGRFF_PIPELINE");   // 0: one pageable copy each way, the kernel bracketed alone by ev0/ev1
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v;
+}
+
+static int host_threads()
+{
+    static int v = 0;
+    if (v == 0) {
+        const char *e = getenv("RTGRFF_HOST_THREADS");
+        int n = e ? atoi(e) : 0;
+        if (n <= 0) {
+            n = (int)std::thread::hardware_concurrency();
+            n = n >= 16 ? 8 : (n >= 4 ? n / 2 : 1);
+        }
+        v = n > 32 ? 32 : n;
+    }
+    return v;
+}
+
+// memcpy split over a few threads (one thread saturates neither the memory channels nor, for fresh
+// numpy output arrays, the page-fault path)
+static void parallel_copy(void *dst, const void *src, size_t bytes)
+{
+    const int nt = host_threads();
+    if (nt <= 1 || bytes < ((size_t)2 << 20)) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    const size_t per = ((bytes / nt) + 4095) & ~(size_t)4095;
+    std::vector<std::thread> th;
+    th.reserve(nt);
+    for (int t = 1; t < nt; ++t) {
+        const size_t o = per * t;
+        if (o >= bytes) break;
+        const size_t len = std::min(per, bytes - o);
+        th.emplace_back([=] { memcpy((char *)dst + o, (const char *)src + o, len); });
+    }
+    memcpy(dst, src, std::min(per, bytes));
+    for (auto &t : th) t.join();
+}
+
+static int pin_reserve(rtgrff_ctx *c, int idx, size_t bytes)
+{
+    if (bytes <= c->pinned_cap[idx]) return RTGRFF_OK;
+    if (c->pinned[idx]) cudaFreeHost(c->pinned[idx]);
+    c->pinned[idx] = nullptr;
+    c->pinned_cap[idx] = 0;
+    cudaError_t e = cudaMallocHost(&c->pinned[idx], bytes);
+    if (e != cudaSuccess) {
+        c->pinned[idx] = nullptr;
+        return fail(RTGRFF_ENOMEM, "cudaMallocHost(%zu) -> %s", bytes, cudaGetErrorString(e));
+    }
+    c->pinned_cap[idx] = bytes;
+    return RTGRFF_OK;
+}
+
+static bool is_pinned_host(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
+// Large device -> host copy: straight DMA when the destination is page-locked, else 32 MB chunks
+// through the two pinned output bounce buffers, the host memcpy of one chunk overlapping the DMA of
+// the next.  Waits for the context's stream first and returns with the data in place.
+static int d2h_large(rtgrff_ctx *c, void *dst, const void *src, size_t bytes)
+{
+    if (!bytes) return RTGRFF_OK;
+    if (is_pinned_host(dst) || bytes < ((size_t)8 << 20) || !pipeline_enabled()) {
+        RT_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+        RT_CUDA(cudaStreamSynchronize(c->stream));
+        return RTGRFF_OK;
+    }
+    const size_t chunk = (size_t)32 << 20;
+    for (int q = 0; q < 2; ++q) RT_TRY(pin_reserve(c, 2 + q, chunk));
+    cudaEvent_t *ev_out = c->chunk_ev + 4;
+    const size_t n_chunk = (bytes + chunk - 1) / chunk;
+    for (size_t k = 0; k <= n_chunk; ++k) {
+        if (k < n_chunk) {
+            const size_t o = k * chunk, len = std::min(chunk, bytes - o);
+            RT_CUDA(cudaMemcpyAsync(c->pinned[2 + (k & 1)], (const char *)src + o, len, cudaMemcpyDeviceToHost, c->stream));
+            RT_CUDA(cudaEventRecord(ev_out[k & 1], c->stream));
+        }
+        if (k >= 1) {
+            const size_t o = (k - 1) * chunk, len = std::min(chunk, bytes - o);
+            RT_CUDA(cudaEventSynchronize(ev_out[(k - 1) & 1]));
+            parallel_copy((char *)dst + o, c->pinned[2 + ((k - 1) & 1)], len);
+        }
+    }
+    return RTGRFF_OK;
+}
+
+// The mirror image for uploads; returns when the source buffer may be reused (not when the DMA is done).
+static int h2d_large(rtgrff_ctx *c, void *dst, const void *src, size_t bytes)
+{
+    if (!bytes) return RTGRFF_OK;
+    if (is_pinned_host(src) || bytes < ((size_t)8 << 20) || !pipeline_enabled()) {
+        RT_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+        return RTGRFF_OK;
+    }
+    const size_t chunk = (size_t)32 << 20;
+    for (int q = 0; q < 2; ++q) RT_TRY(pin_reserve(c, q, chunk));
+    cudaEvent_t *ev_in = c->chunk_ev;
+    const size_t n_chunk = (bytes + chunk - 1) / chunk;
+    for (size_t k = 0; k < n_chunk; ++k) {
+        const size_t o = k * chunk, len = std::min(chunk, bytes - o);
+        if (k >= 2) RT_CUDA(cudaEventSynchronize(ev_in[k & 1]));
+        parallel_copy(c->pinned[k & 1], (const char *)src + o, len);
+        RT_CUDA(cudaMemcpyAsync((char *)dst + o, c->pinned[k & 1], len, cudaMemcpyHostToDevice, c->stream));
+        RT_CUDA(cudaEventRecord(ev_in[k & 1], c->stream));
+    }
+    // the bounce buffers are reused by the next call: drain them before returning
+    RT_CUDA(cudaEventSynchronize(ev_in[(n_chunk - 1) & 1]));
+    if (n_chunk >= 2) RT_CUDA(cudaEventSynchronize(ev_in[(n_chunk - 2) & 1]));
+    return RTGRFF_OK;
+}
+
+constexpr size_t kPipeMinBytes = (size_t)16 << 20;    // below this a call is one plain copy each way
+constexpr size_t kPipeChunkBytes = (size_t)32 << 20;  // bounce-buffer size per direction and stage
 
 static int launched(rtgrff_ctx *c, const char *what)
 {
@@ -170,45 +329,83 @@ int rtgrff_device_count(void)
     return n;
 }
 
-int rtgrff_ctx_create(int device, void *stream, rtgrff_ctx **out)
+static int ctx_create(int device, void *stream, bool caller_stream, rtgrff_ctx **out)
 {
     if (!out) return fail(RTGRFF_EINVAL, "out is null");
     *out = nullptr;
     int n = 0;
     RT_CUDA(cudaGetDeviceCount(&n));
     if (device < 0 || device >= n) return fail(RTGRFF_EINVAL, "device %d out of range (%d visible)", device, n);
-    RT_CUDA(cudaSetDevice(device));
+    DeviceGuard guard;
+    RT_TRY(guard.enter_device(device));
     rtgrff_ctx *c = new (std::nothrow) rtgrff_ctx();
     if (!c) return fail(RTGRFF_ENOMEM, "out of host memory");
     c->device = device;
+    cudaError_t e = cudaSuccess;
     cudaDeviceProp prop;
-    RT_CUDA(cudaGetDeviceProperties(&prop, device));
-    c->sm_count = prop.multiProcessorCount;
-    if (stream) {
-        c->stream = (cudaStream_t)stream;
-    } else {
-        RT_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-        c->own_stream = true;
+    if ((e = cudaGetDeviceProperties(&prop, device)) == cudaSuccess) {
+        c->sm_count = prop.multiProcessorCount;
+        if (caller_stream) {
+            c->stream = (cudaStream_t)stream;      // including 0: the legacy default stream
+        } else if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) == cudaSuccess) {
+            c->own_stream = true;
+        }
     }
-    RT_CUDA(cudaEventCreate(&c->ev0));
-    RT_CUDA(cudaEventCreate(&c->ev1));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    for (int q = 0; q < 6 && e == cudaSuccess; ++q) e = cudaEventCreateWithFlags(&c->chunk_ev[q], cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        rtgrff_ctx_destroy(c);
+        return fail(RTGRFF_ECUDA, "rtgrff_ctx_create -> %s", cudaGetErrorString(e));
+    }
     *out = c;
     return RTGRFF_OK;
+}
+
+int rtgrff_ctx_create(int device, void *stream, rtgrff_ctx **out)
+{
+    return ctx_create(device, stream, stream != nullptr, out);
+}
+
+int rtgrff_ctx_create_on_stream(int device, void *stream, rtgrff_ctx **out)
+{
+    return ctx_create(device, stream, true, out);
+}
+
+int rtgrff_current_device(void)
+{
+    int d = -1;
+    cudaError_t e = cudaGetDevice(&d);
+    if (e != cudaSuccess) return fail(RTGRFF_ECUDA, "cudaGetDevice -> %s", cudaGetErrorString(e));
+    return d;
 }
 
 int rtgrff_ctx_destroy(rtgrff_ctx *c)
 {
     if (!c) return RTGRFF_OK;
-    cudaSetDevice(c->device);
+    DeviceGuard guard;
+    guard.enter_device(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    if (c->comm) {
+        NcclApi *n = nccl_api();
+        if (n) n->CommDestroy((NcclComm)c->comm);
+        c->comm = nullptr;
+    }
     DevBuf *bufs[] = {&c->wcube, &c->pcube, &c->fcube, &c->bcube, &c->rec_pos, &c->rec_s, &c->smp_ne, &c->smp_te, &c->smp_b,
                       &c->smp_ds, &c->smp_s, &c->smp_valid, &c->in0, &c->in1, &c->in2, &c->in3, &c->out0, &c->out1,
-                      &c->out2, &c->out3, &c->out4, &c->out5, &c->stage, &c->counters};
+                      &c->out2, &c->out3, &c->out4, &c->out5, &c->stage, &c->counters, &c->gather_buf, &c->image_buf};
     for (DevBuf *b : bufs) b->release();
     for (DevBuf &b : c->slot) b.release();
     c->slot_grids.release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    for (cudaEvent_t &e : c->chunk_ev)
+        if (e) cudaEventDestroy(e);
+    for (void *&h : c->pinned)
+        if (h) cudaFreeHost(h);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return RTGRFF_OK;
@@ -216,7 +413,7 @@ int rtgrff_ctx_destroy(rtgrff_ctx *c)
 
 int rtgrff_ctx_synchronize(rtgrff_ctx *c)
 {
-    RT_TRY(use(c));
+    RT_USE(c);
     RT_CUDA(cudaStreamSynchronize(c->stream));
     return RTGRFF_OK;
 }
@@ -227,7 +424,8 @@ double rtgrff_ctx_last_kernel_ms(rtgrff_ctx *c)
 {
     if (!c || !c->ev_valid) return -1.0;
     float ms = -1.0f;
-    if (cudaSetDevice(c->device) != cudaSuccess) return -1.0;
+    DeviceGuard guard;
+    if (guard.enter_device(c->device) != RTGRFF_OK) return -1.0;
     if (cudaEventSynchronize(c->ev1) != cudaSuccess) return -1.0;
     if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) != cudaSuccess) return -1.0;
     return (double)ms;
@@ -236,16 +434,18 @@ double rtgrff_ctx_last_kernel_ms(rtgrff_ctx *c)
 int rtgrff_set_omega_cube(rtgrff_ctx *c, const double *omega_pe, int nx, int ny, int nz, const double geom[12],
                           int on_device)
 {
-    RT_TRY(use(c));
+    RT_USE(c);
     if (!omega_pe || !geom) return fail(RTGRFF_EINVAL, "null argument");
     GridGeom g;
     RT_TRY(geom_from(geom, nx, ny, nz, g));
     const size_t nvox = (size_t)nx * ny * nz;
     const double *src = omega_pe;
     if (!on_device) {
-        RT_TRY(h2d(c, c->stage, omega_pe, nvox * sizeof(double)));
+        RT_TRY(c->stage.reserve(nvox * sizeof(double)));
+        RT_TRY(h2d_large(c, c->stage.p, omega_pe, nvox * sizeof(double)));
         src = c->stage.as<double>();
     }
+    c->stage_has_omega = !on_device;
     RT_TRY(c->wcube.reserve(nvox * sizeof(float4)));
     build_ray_cube_kernel<<<blocks_for((int64_t)nvox, 256), 256, 0, c->stream>>>(src, c->wcube.as<float4>(), nx, ny, nz,
                                                                                  geom[3], geom[7], geom[11]);
@@ -260,7 +460,7 @@ int rtgrff_set_omega_cube(rtgrff_ctx *c, const double *omega_pe, int nx, int ny,
 int rtgrff_set_field_cubes(rtgrff_ctx *c, const float *ne, const float *te, const float *b, const float *bx,
                            const float *by, const float *bz, int nx, int ny, int nz, const double geom[12])
 {
-    RT_TRY(use(c));
+    RT_USE(c);
     if (!ne || !te || !b || !geom) return fail(RTGRFF_EINVAL, "null argument");
     const bool bvec = bx && by && bz;
     if ((bx || by || bz) && !bvec) return fail(RTGRFF_EINVAL, "bx, by, bz must be given together");
@@ -268,18 +468,19 @@ int rtgrff_set_field_cubes(rtgrff_ctx *c, const float *ne, const float *te, cons
     RT_TRY(geom_from(geom, nx, ny, nz, g));
     const size_t nvox = (size_t)nx * ny * nz, fb = nvox * sizeof(float);
     RT_TRY(c->stage.reserve(3 * fb));
+    c->stage_has_omega = false;
     float *s0 = c->stage.as<float>(), *s1 = s0 + nvox, *s2 = s1 + nvox;
     RT_TRY(c->fcube.reserve(nvox * sizeof(float4)));
-    RT_CUDA(cudaMemcpyAsync(s0, ne, fb, cudaMemcpyHostToDevice, c->stream));
-    RT_CUDA(cudaMemcpyAsync(s1, te, fb, cudaMemcpyHostToDevice, c->stream));
-    RT_CUDA(cudaMemcpyAsync(s2, b, fb, cudaMemcpyHostToDevice, c->stream));
+    RT_TRY(h2d_large(c, s0, ne, fb));
+    RT_TRY(h2d_large(c, s1, te, fb));
+    RT_TRY(h2d_large(c, s2, b, fb));
     interleave3_kernel<<<blocks_for((int64_t)nvox, 256), 256, 0, c->stream>>>(s0, s1, s2, c->fcube.as<float4>(), (int64_t)nvox);
     RT_TRY(launched(c, "interleave3_kernel"));
     if (bvec) {
         RT_TRY(c->bcube.reserve(nvox * sizeof(float4)));
-        RT_CUDA(cudaMemcpyAsync(s0, bx, fb, cudaMemcpyHostToDevice, c->stream));
-        RT_CUDA(cudaMemcpyAsync(s1, by, fb, cudaMemcpyHostToDevice, c->stream));
-        RT_CUDA(cudaMemcpyAsync(s2, bz, fb, cudaMemcpyHostToDevice, c->stream));
+        RT_TRY(h2d_large(c, s0, bx, fb));
+        RT_TRY(h2d_large(c, s1, by, fb));
+        RT_TRY(h2d_large(c, s2, bz, fb));
         interleave3_kernel<<<blocks_for((int64_t)nvox, 256), 256, 0, c->stream>>>(s0, s1, s2, c->bcube.as<float4>(), (int64_t)nvox);
         RT_TRY(launched(c, "interleave3_kernel"));
     }
@@ -301,7 +502,7 @@ int rtgrff_resample_spherical(rtgrff_ctx *c, int slot, const float *data, const 
                               double phi0_offset_deg, double r_min, double scale, double fill, int fill_nonfinite,
                               double *out)
 {
-    RT_TRY(use(c));
+    RT_USE(c);
     if (slot < 0 || slot > 4) return fail(RTGRFF_EINVAL, "slot %d out of range 0..4", slot);
     if (!data || !phi || !lat || !r || !geom || !x_grid || !y_grid || !z_grid) return fail(RTGRFF_EINVAL, "null argument");
     if (np < 2 || nt < 2 || nr < 2) return fail(RTGRFF_EINVAL, "spherical mesh needs >= 2 nodes per axis");
@@ -347,6 +548,7 @@ int rtgrff_resample_spherical(rtgrff_ctx *c, int slot, const float *data, const 
     c->slot_set[slot] = true;
     c->slot_nx = nx; c->slot_ny = ny; c->slot_nz = nz;
     memcpy(c->slot_geom, geom, sizeof(c->slot_geom));
+    memcpy(c->slot_geoms[slot], geom, sizeof(c->slot_geom));
     return RTGRFF_OK;
 }
 
@@ -355,7 +557,7 @@ int rtgrff_sample_spherical_los(rtgrff_ctx *c, const float *data, const double *
                                 int ny, int nz, double phi0_offset_deg, double r_min, double scale, double z_eps,
                                 double *out)
 {
-    RT_TRY(use(c));
+    RT_USE(c);
     if (!data || !phi || !lat || !r || !x || !y || !zc || !out) return fail(RTGRFF_EINVAL, "null argument");
     if (np < 2 || nt < 2 || nr < 2 || nx < 1 || ny < 1 || nz < 1) return fail(RTGRFF_EINVAL, "bad sizes");
     for (int i = 1; i < np; ++i) if (!(phi[i] > phi[i - 1])) return fail(RTGRFF_EINVAL, "phi nodes must ascend");
@@ -399,11 +601,14 @@ int rtgrff_sample_spherical_los(rtgrff_ctx *c, const float *data, const double *
 
 int rtgrff_compose_cubes(rtgrff_ctx *c, int want_bvec)
 {
-    RT_TRY(use(c));
+    RT_USE(c);
     for (int s = 0; s < 5; ++s)
         if (!c->slot_set[s]) return fail(RTGRFF_ENOCUBE, "spherical slot %d (0 rho, 1 te, 2 br, 3 bt, 4 bp) is not set", s);
     const int nx = c->slot_nx, ny = c->slot_ny, nz = c->slot_nz;
     const double *geom = c->slot_geom;
+    for (int s = 0; s < 5; ++s)
+        if (memcmp(c->slot_geoms[s], geom, sizeof(c->slot_geom)) != 0)
+            return fail(RTGRFF_EINVAL, "spherical slot %d was resampled on a different cube geometry than the last one", s);
     GridGeom g;
     RT_TRY(geom_from(geom, nx, ny, nz, g));
     const size_t nvox = (size_t)nx * ny * nz;
@@ -434,6 +639,7 @@ int rtgrff_compose_cubes(rtgrff_ctx *c, int want_bvec)
     f.idx = (float)(1.0 / geom[1]); f.idy = (float)(1.0 / geom[5]); f.idz = (float)(1.0 / geom[9]);
     f.fxl = (float)(nx - 1); f.fyl = (float)(ny - 1); f.fzl = (float)(nz - 1);
     c->has_wcube = true; c->has_fcube = true; c->has_bvec = want_bvec != 0;
+    c->stage_has_omega = true;
     return RTGRFF_OK;
 }
 
@@ -441,7 +647,7 @@ int rtgrff_trace(rtgrff_ctx *c, int64_t n_rays, const double *x_start, const dou
                  const double *kvec, double freq_hz, double dt, int64_t n_steps, int64_t record_stride, int trace_cs,
                  double perturb_ratio, int s_mode, double *r_record, double *s_record, int64_t *active_steps)
 {
-    RT_TRY(use(c));
+    RT_USE(c);
     if (!c->has_wcube) return fail(RTGRFF_ENOCUBE, "rtgrff_set_omega_cube has not been called");
     if (n_rays < 0 || n_steps < 0 || record_stride < 1) return fail(RTGRFF_EINVAL, "bad n_rays/n_steps/record_stride");
     if (n_rays > 0 && (!x_start || !y_start || !z_start)) return fail(RTGRFF_EINVAL, "null start arrays");
@@ -505,7 +711,7 @@ int rtgrff_trace(rtgrff_ctx *c, int64_t n_rays, const double *x_start, const dou
     return RTGRFF_OK;
 }
 
-static int run_sampler(rtgrff_ctx *c, SampleArgs &a, double r_sun_cm, double fill_ne, double fill_te, double fill_b)
+static int prepare_sampler(rtgrff_ctx *c, SampleArgs &a, double r_sun_cm, double fill_ne, double fill_te, double fill_b)
 {
     const size_t n = (size_t)a.n_rec * a.n_rays;
     RT_TRY(c->smp_ne.reserve(n * 4)); RT_TRY(c->smp_te.reserve(n * 4)); RT_TRY(c->smp_b.reserve(n * 4));
@@ -516,15 +722,27 @@ static int run_sampler(rtgrff_ctx *c, SampleArgs &a, double r_sun_cm, double fil
     a.fill_ne = (float)fill_ne; a.fill_te = (float)fill_te; a.fill_b = (float)fill_b;
     a.ne = c->smp_ne.as<float>(); a.te = c->smp_te.as<float>(); a.b = c->smp_b.as<float>();
     a.ds = c->smp_ds.as<float>(); a.s_out = c->smp_s.as<float>(); a.valid = c->smp_valid.as<uint8_t>();
-    unsigned int blocks = blocks_for((int64_t)n, 256);
+    a.q_begin = 0; a.q_end = 0;
+    c->smp_n = a.n_rec; c->smp_rays = a.n_rays;
+    return RTGRFF_OK;
+}
+
+static int launch_sampler(rtgrff_ctx *c, const SampleArgs &a, int64_t count)
+{
+    unsigned int blocks = blocks_for(count, 256);
     const unsigned int cap = (unsigned int)c->sm_count * 64;
     if (blocks > cap) blocks = cap;
-    RT_CUDA(cudaEventRecord(c->ev0, c->stream));
     sample_paths_kernel<<<blocks, 256, 0, c->stream>>>(a);
-    RT_TRY(launched(c, "sample_paths_kernel"));
+    return launched(c, "sample_paths_kernel");
+}
+
+static int run_sampler(rtgrff_ctx *c, SampleArgs &a, double r_sun_cm, double fill_ne, double fill_te, double fill_b)
+{
+    RT_TRY(prepare_sampler(c, a, r_sun_cm, fill_ne, fill_te, fill_b));
+    RT_CUDA(cudaEventRecord(c->ev0, c->stream));
+    RT_TRY(launch_sampler(c, a, a.n_rec * a.n_rays));
     RT_CUDA(cudaEventRecord(c->ev1, c->stream));
     c->ev_valid = true;
-    c->smp_n = a.n_rec; c->smp_rays = a.n_rays;
     return RTGRFF_OK;
 }
 
@@ -540,22 +758,90 @@ static int sampler_out(rtgrff_ctx *c, size_t n, float *ne, float *te, float *b, 
     return RTGRFF_OK;
 }
 
+// rtgrff_sample on large host arrays: record-range chunks through the pinned bounce buffers (see the
+// pipeline note above).  A chunk's ds looks back at earlier records, which are on the device already
+// (chunks go up in order on one stream).
+static int sample_pipelined(rtgrff_ctx *c, SampleArgs &a, const float *pos, const float *s, float *ne, float *te,
+                            float *b, float *ds, uint8_t *valid)
+{
+    const int64_t n_rec = a.n_rec, n_rays = a.n_rays;
+    const size_t per_rec_in = (size_t)n_rays * 16, per_rec_out = (size_t)n_rays * 17;
+    int64_t rec_per_chunk = (int64_t)(kPipeChunkBytes / per_rec_out);
+    if (rec_per_chunk < 1) rec_per_chunk = 1;
+    const int64_t n_chunk = (n_rec + rec_per_chunk - 1) / rec_per_chunk;
+    const size_t cin = (size_t)rec_per_chunk * per_rec_in, cout = (size_t)rec_per_chunk * per_rec_out;
+    for (int q = 0; q < 2; ++q) {
+        RT_TRY(pin_reserve(c, q, cin));
+        RT_TRY(pin_reserve(c, 2 + q, cout));
+    }
+    cudaEvent_t *ev_in = c->chunk_ev, *ev_k = c->chunk_ev + 2, *ev_out = c->chunk_ev + 4;
+    float *d_pos = c->in0.as<float>(), *d_s = c->in1.as<float>();
+    auto unpack = [&](int64_t k) {
+        const int64_t r0 = k * rec_per_chunk, r1 = std::min(n_rec, r0 + rec_per_chunk);
+        const size_t q0 = (size_t)r0 * n_rays, cnt = (size_t)(r1 - r0) * n_rays;
+        const char *src = (const char *)c->pinned[2 + (k & 1)];
+        float *outs[4] = {ne, te, b, ds};
+        for (int m = 0; m < 4; ++m)
+            if (outs[m]) parallel_copy(outs[m] + q0, src + (size_t)m * cnt * 4, cnt * 4);
+        if (valid) parallel_copy(valid + q0, src + (size_t)4 * cnt * 4, cnt);
+    };
+    RT_CUDA(cudaEventRecord(c->ev0, c->stream));
+    for (int64_t k = 0; k < n_chunk; ++k) {
+        const int bsel = (int)(k & 1);
+        const int64_t r0 = k * rec_per_chunk, r1 = std::min(n_rec, r0 + rec_per_chunk);
+        const size_t q0 = (size_t)r0 * n_rays, cnt = (size_t)(r1 - r0) * n_rays;
+        if (k >= 2) RT_CUDA(cudaEventSynchronize(ev_in[bsel]));
+        char *pin = (char *)c->pinned[bsel];
+        parallel_copy(pin, pos + q0 * 3, cnt * 12);
+        parallel_copy(pin + cnt * 12, s + q0, cnt * 4);
+        RT_CUDA(cudaMemcpyAsync(d_pos + q0 * 3, pin, cnt * 12, cudaMemcpyHostToDevice, c->stream));
+        RT_CUDA(cudaMemcpyAsync(d_s + q0, pin + cnt * 12, cnt * 4, cudaMemcpyHostToDevice, c->stream));
+        RT_CUDA(cudaEventRecord(ev_in[bsel], c->stream));
+        a.q_begin = (int64_t)q0; a.q_end = (int64_t)(q0 + cnt);
+        RT_TRY(launch_sampler(c, a, (int64_t)cnt));
+        RT_CUDA(cudaEventRecord(ev_k[bsel], c->stream));
+        RT_CUDA(cudaStreamWaitEvent(c->copy_stream, ev_k[bsel], 0));
+        char *pout = (char *)c->pinned[2 + bsel];
+        const float *outs[4] = {a.ne, a.te, a.b, a.ds};
+        for (int m = 0; m < 4; ++m)
+            RT_CUDA(cudaMemcpyAsync(pout + (size_t)m * cnt * 4, outs[m] + q0, cnt * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+        RT_CUDA(cudaMemcpyAsync(pout + (size_t)4 * cnt * 4, a.valid + q0, cnt, cudaMemcpyDeviceToHost, c->copy_stream));
+        RT_CUDA(cudaEventRecord(ev_out[bsel], c->copy_stream));
+        if (k >= 1) {
+            RT_CUDA(cudaEventSynchronize(ev_out[1 - bsel]));
+            unpack(k - 1);
+        }
+    }
+    RT_CUDA(cudaEventRecord(c->ev1, c->stream));
+    c->ev_valid = true;
+    RT_CUDA(cudaEventSynchronize(ev_out[(n_chunk - 1) & 1]));
+    unpack(n_chunk - 1);
+    RT_CUDA(cudaStreamSynchronize(c->stream));
+    return RTGRFF_OK;
+}
+
 int rtgrff_sample(rtgrff_ctx *c, int64_t n_rec, int64_t n_rays, const float *pos, const float *s,
                   const float *ray_start, double r_sun_cm, double fill_ne, double fill_te, double fill_b, float *ne,
                   float *te, float *b, float *ds, uint8_t *valid)
 {
-    RT_TRY(use(c));
+    RT_USE(c);
     if (!c->has_fcube) return fail(RTGRFF_ENOCUBE, "rtgrff_set_field_cubes has not been called");
     if (n_rec < 0 || n_rays < 0) return fail(RTGRFF_EINVAL, "negative sizes");
     const size_t n = (size_t)n_rec * n_rays;
     if (n == 0) return RTGRFF_OK;
     if (!pos || !s || !ray_start) return fail(RTGRFF_EINVAL, "null input");
-    RT_TRY(h2d(c, c->in0, pos, n * 3 * sizeof(float)));
-    RT_TRY(h2d(c, c->in1, s, n * sizeof(float)));
-    RT_TRY(h2d(c, c->in2, ray_start, (size_t)n_rays * 3 * sizeof(float)));
     SampleArgs a{};
     a.n_rec = n_rec; a.n_rays = n_rays;
+    RT_TRY(c->in0.reserve(n * 3 * sizeof(float)));
+    RT_TRY(c->in1.reserve(n * sizeof(float)));
+    RT_TRY(h2d(c, c->in2, ray_start, (size_t)n_rays * 3 * sizeof(float)));
     a.pos_aos = c->in0.as<float>(); a.s32 = c->in1.as<float>(); a.ray_start = c->in2.as<float>();
+    if (pipeline_enabled() && n * 33 >= kPipeMinBytes) {
+        RT_TRY(prepare_sampler(c, a, r_sun_cm, fill_ne, fill_te, fill_b));
+        return sample_pipelined(c, a, pos, s, ne, te, b, ds, valid);
+    }
+    RT_TRY(h2d(c, c->in0, pos, n * 3 * sizeof(float)));
+    RT_TRY(h2d(c, c->in1, s, n * sizeof(float)));
     RT_TRY(run_sampler(c, a, r_sun_cm, fill_ne, fill_te, fill_b));
     return sampler_out(c, n, ne, te, b, ds, valid, nullptr);
 }
@@ -563,7 +849,7 @@ int rtgrff_sample(rtgrff_ctx *c, int64_t n_rec, int64_t n_rays, const float *pos
 int rtgrff_sample_traced(rtgrff_ctx *c, const float *ray_start, double r_sun_cm, double fill_ne, double fill_te,
                          double fill_b, float *ne, float *te, float *b, float *ds, uint8_t *valid, float *s)
 {
-    RT_TRY(use(c));
+    RT_USE(c);
     if (!c->has_fcube) return fail(RTGRFF_ENOCUBE, "rtgrff_set_field_cubes has not been called");
     if (c->rec_n <= 0 || c->rec_rays <= 0) return fail(RTGRFF_EINVAL, "no traced records on the device");
     if (!ray_start) return fail(RTGRFF_EINVAL, "null ray_start");
@@ -578,25 +864,66 @@ int rtgrff_sample_traced(rtgrff_ctx *c, const float *ray_start, double r_sun_cm,
     return sampler_out(c, n, ne, te, b, ds, valid, s);
 }
 
-static int run_slice(rtgrff_ctx *c, int npix, int nz, int nf, const double *rparms, const double *parms, double *rl,
-                     int32_t *status)
+static int launch_slice(rtgrff_ctx *c, const double *parms, const double *rparms, double *rl, int32_t *status, int npix,
+                        int nz, int nf)
 {
-    const size_t pb = (size_t)15 * nz * npix * sizeof(double), rb = (size_t)3 * npix * sizeof(double);
+    SliceArgs a;
+    a.parms = parms; a.rparms = rparms; a.rl = rl; a.status = status;
+    a.npix = npix; a.nz = nz; a.nf = nf;
+    const int64_t warps = (int64_t)npix * nf;
+    grff_slice_kernel<<<blocks_for(warps * 32, 128), 128, 0, c->stream>>>(a);
+    return launched(c, "grff_slice_kernel");
+}
+
+// on_device: Rparms / Parms / RL / status are device pointers (the fastGRFF contract: CuPy arrays in,
+// RL_M written in place on the device, script/resample_with_ray_tracing.py:428-446); else host arrays,
+// large ones moved in pixel chunks through the pinned bounce buffers while earlier chunks compute.
+static int run_slice(rtgrff_ctx *c, int npix, int nz, int nf, const double *rparms, const double *parms, double *rl,
+                     int32_t *status, int on_device)
+{
+    const size_t pix_b = (size_t)15 * nz * sizeof(double);
+    const size_t pb = pix_b * npix, rb = (size_t)3 * npix * sizeof(double);
     const size_t ob = (size_t)7 * nf * npix * sizeof(double);
-    RT_TRY(h2d(c, c->in0, parms, pb));
+    if (on_device) {
+        if (status) RT_CUDA(cudaMemsetAsync(status, 0xff, (size_t)npix * sizeof(int32_t), c->stream));
+        RT_CUDA(cudaEventRecord(c->ev0, c->stream));
+        RT_TRY(launch_slice(c, parms, rparms, rl, status, npix, nz, nf));
+        RT_CUDA(cudaEventRecord(c->ev1, c->stream));
+        c->ev_valid = true;
+        RT_CUDA(cudaStreamSynchronize(c->stream));
+        return RTGRFF_OK;
+    }
+    RT_TRY(c->in0.reserve(pb ? pb : 1));
     RT_TRY(h2d(c, c->in1, rparms, rb));
     RT_TRY(c->out0.reserve(ob));
     RT_TRY(c->out1.reserve((size_t)npix * sizeof(int32_t)));
     RT_CUDA(cudaMemsetAsync(c->out1.p, 0xff, (size_t)npix * sizeof(int32_t), c->stream));
-    SliceArgs a;
-    a.parms = c->in0.as<double>(); a.rparms = c->in1.as<double>();
-    a.rl = c->out0.as<double>(); a.status = c->out1.as<int32_t>();
-    a.npix = npix; a.nz = nz; a.nf = nf;
-    const int64_t warps = (int64_t)npix * nf;
-    RT_CUDA(cudaEventRecord(c->ev0, c->stream));
-    grff_slice_kernel<<<blocks_for(warps * 32, 128), 128, 0, c->stream>>>(a);
-    RT_TRY(launched(c, "grff_slice_kernel"));
-    RT_CUDA(cudaEventRecord(c->ev1, c->stream));
+    double *d_parms = c->in0.as<double>();
+    if (pipeline_enabled() && pb >= kPipeMinBytes && pix_b > 0) {
+        int64_t pix_per_chunk = (int64_t)(kPipeChunkBytes / pix_b);
+        if (pix_per_chunk < 1) pix_per_chunk = 1;
+        const int64_t n_chunk = (npix + pix_per_chunk - 1) / pix_per_chunk;
+        for (int q = 0; q < 2; ++q) RT_TRY(pin_reserve(c, q, (size_t)pix_per_chunk * pix_b));
+        cudaEvent_t *ev_in = c->chunk_ev;
+        RT_CUDA(cudaEventRecord(c->ev0, c->stream));
+        for (int64_t k = 0; k < n_chunk; ++k) {
+            const int bsel = (int)(k & 1);
+            const int64_t p0 = k * pix_per_chunk, p1 = std::min<int64_t>(npix, p0 + pix_per_chunk);
+            const size_t bytes = (size_t)(p1 - p0) * pix_b;
+            if (k >= 2) RT_CUDA(cudaEventSynchronize(ev_in[bsel]));
+            parallel_copy(c->pinned[bsel], (const char *)parms + (size_t)p0 * pix_b, bytes);
+            RT_CUDA(cudaMemcpyAsync((char *)d_parms + (size_t)p0 * pix_b, c->pinned[bsel], bytes, cudaMemcpyHostToDevice, c->stream));
+            RT_CUDA(cudaEventRecord(ev_in[bsel], c->stream));
+            RT_TRY(launch_slice(c, d_parms + (size_t)p0 * 15 * nz, c->in1.as<double>() + (size_t)p0 * 3,
+                                c->out0.as<double>() + (size_t)p0 * 7 * nf, c->out1.as<int32_t>() + p0, (int)(p1 - p0), nz, nf));
+        }
+        RT_CUDA(cudaEventRecord(c->ev1, c->stream));
+    } else {
+        if (pb) RT_CUDA(cudaMemcpyAsync(d_parms, parms, pb, cudaMemcpyHostToDevice, c->stream));
+        RT_CUDA(cudaEventRecord(c->ev0, c->stream));
+        RT_TRY(launch_slice(c, d_parms, c->in1.as<double>(), c->out0.as<double>(), c->out1.as<int32_t>(), npix, nz, nf));
+        RT_CUDA(cudaEventRecord(c->ev1, c->stream));
+    }
     c->ev_valid = true;
     RT_TRY(d2h(c, rl, c->out0.p, ob));
     if (status) RT_TRY(d2h(c, status, c->out1.p, (size_t)npix * sizeof(int32_t)));
@@ -604,20 +931,94 @@ static int run_slice(rtgrff_ctx *c, int npix, int nz, int nf, const double *rpar
     return RTGRFF_OK;
 }
 
+static int slice_sizes(const int32_t *L, int &npix, int &nz, int &nf)
+{
+    npix = L[0]; nz = L[1]; nf = L[2];
+    if (npix < 0 || nz < 0 || nf <= 0) return fail(RTGRFF_EINVAL, "bad Lparms_M {%d,%d,%d}", npix, nz, nf);
+    if (L[3] > 1 || L[4] != 0 || L[5] != 0) return fail(RTGRFF_EUNSUPPORTED, "DEM / DDM inputs are not supported (Lparms_M[3..5] = {%d,%d,%d})", L[3], L[4], L[5]);
+    return RTGRFF_OK;
+}
+
 int rtgrff_get_mw_slice(rtgrff_ctx *c, const int32_t *Lparms_M, const double *Rparms_M, const double *Parms_M,
                         const double *T_arr, const double *DEM_arr, const double *DDM_arr, double *RL_M, int32_t *status)
 {
     (void)T_arr; (void)DEM_arr; (void)DDM_arr;
-    RT_TRY(use(c));
+    RT_USE(c);
     if (!Lparms_M || !Rparms_M || !Parms_M || !RL_M) return fail(RTGRFF_EINVAL, "null argument");
-    const int npix = Lparms_M[0], nz = Lparms_M[1], nf = Lparms_M[2];
-    if (npix < 0 || nz < 0 || nf <= 0) return fail(RTGRFF_EINVAL, "bad Lparms_M {%d,%d,%d}", npix, nz, nf);
+    int npix, nz, nf;
+    RT_TRY(slice_sizes(Lparms_M, npix, nz, nf));
     if (npix == 0) return RTGRFF_OK;
-    return run_slice(c, npix, nz, nf, Rparms_M, Parms_M, RL_M, status);
+    return run_slice(c, npix, nz, nf, Rparms_M, Parms_M, RL_M, status, 0);
+}
+
+int rtgrff_get_mw_slice_device(rtgrff_ctx *c, const int32_t *Lparms_M, const double *Rparms_M_dev,
+                               const double *Parms_M_dev, double *RL_M_dev, int32_t *status_dev)
+{
+    RT_USE(c);
+    if (!Lparms_M || !Rparms_M_dev || !Parms_M_dev || !RL_M_dev) return fail(RTGRFF_EINVAL, "null argument");
+    int npix, nz, nf;
+    RT_TRY(slice_sizes(Lparms_M, npix, nz, nf));
+    if (npix == 0) return RTGRFF_OK;
+    return run_slice(c, npix, nz, nf, Rparms_M_dev, Parms_M_dev, RL_M_dev, status_dev, 1);
+}
+
+int rtgrff_device_alloc(rtgrff_ctx *c, void **out, size_t bytes)
+{
+    RT_USE(c);
+    if (!out) return fail(RTGRFF_EINVAL, "null argument");
+    *out = nullptr;
+    cudaError_t e = cudaMalloc(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? RTGRFF_ENOMEM : RTGRFF_ECUDA, "cudaMalloc(%zu) -> %s", bytes, cudaGetErrorString(e));
+    return RTGRFF_OK;
+}
+
+int rtgrff_device_free(rtgrff_ctx *c, void *p)
+{
+    RT_USE(c);
+    if (p) RT_CUDA(cudaFree(p));
+    return RTGRFF_OK;
+}
+
+int rtgrff_memcpy(rtgrff_ctx *c, void *dst, const void *src, size_t bytes, int kind)
+{
+    RT_USE(c);
+    if ((!dst || !src) && bytes) return fail(RTGRFF_EINVAL, "null argument");
+    const cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : (kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice);
+    if (kind < 0 || kind > 2) return fail(RTGRFF_EINVAL, "kind must be 0 (H2D), 1 (D2H) or 2 (D2D)");
+    if (bytes) RT_CUDA(cudaMemcpyAsync(dst, src, bytes, k, c->stream));
+    RT_CUDA(cudaStreamSynchronize(c->stream));
+    return RTGRFF_OK;
+}
+
+int rtgrff_export_cubes(rtgrff_ctx *c, double *omega_pe, float *ne, float *te, float *b, float *bx, float *by, float *bz)
+{
+    RT_USE(c);
+    if (omega_pe) {
+        if (!c->has_wcube) return fail(RTGRFF_ENOCUBE, "no ray cube on the device");
+        if (!c->stage_has_omega) return fail(RTGRFF_EUNSUPPORTED, "the float64 omega_pe of the last cube build is no longer staged on the device");
+        const size_t n = (size_t)c->wgeom.nx * c->wgeom.ny * c->wgeom.nz;
+        RT_TRY(d2h(c, omega_pe, c->stage.p, n * sizeof(double)));
+        RT_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    for (int pass = 0; pass < 2; ++pass) {
+        float *o[3] = {pass ? bx : ne, pass ? by : te, pass ? bz : b};
+        if (!o[0] && !o[1] && !o[2]) continue;
+        if (pass ? !c->has_bvec : !c->has_fcube) return fail(RTGRFF_ENOCUBE, "no %s cube on the device", pass ? "B-vector" : "field");
+        const size_t n = (size_t)c->fgeom.nx * c->fgeom.ny * c->fgeom.nz;
+        RT_TRY(c->out3.reserve(3 * n * sizeof(float)));
+        float *d = c->out3.as<float>();
+        deinterleave3_kernel<<<blocks_for((int64_t)n, 256), 256, 0, c->stream>>>((pass ? c->bcube : c->fcube).as<float4>(), d,
+                                                                                  d + n, d + 2 * n, (int64_t)n);
+        RT_TRY(launched(c, "deinterleave3_kernel"));
+        for (int m = 0; m < 3; ++m)
+            if (o[m]) RT_TRY(d2h(c, o[m], d + (size_t)m * n, n * sizeof(float)));
+        RT_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return RTGRFF_OK;
 }
 
 static std::mutex g_default_mu;
-static rtgrff_ctx *g_default_ctx = nullptr;
+static rtgrff_ctx *g_default_ctx[64] = {nullptr};   // one process-wide context per device, made on first use
 
 int PyGET_MW(const int32_t *Lparms, const double *Rparms, const double *Parms, const double *T_arr,
              const double *DEM_arr, const double *DDM_arr, double *RL)
@@ -628,15 +1029,16 @@ int PyGET_MW(const int32_t *Lparms, const double *Rparms, const double *Parms, c
     if (nz < 0 || nf <= 0) return 1;
     if (Lparms[2] > 0) return 2;
     std::lock_guard<std::mutex> lk(g_default_mu);
-    if (!g_default_ctx && rtgrff_ctx_create(0, nullptr, &g_default_ctx) != RTGRFF_OK) return 3;
-    if (use(g_default_ctx) != RTGRFF_OK) return 3;
-    return run_slice(g_default_ctx, 1, nz, nf, Rparms, Parms, RL, nullptr) == RTGRFF_OK ? 0 : 3;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 3;   // the caller's current device
+    if (!g_default_ctx[dev] && rtgrff_ctx_create(dev, nullptr, &g_default_ctx[dev]) != RTGRFF_OK) return 3;
+    return run_slice(g_default_ctx[dev], 1, nz, nf, Rparms, Parms, RL, nullptr, 0) == RTGRFF_OK ? 0 : 3;
 }
 
 int rtgrff_emission_traced(rtgrff_ctx *c, double pixel_area_cm2, double freq0_hz, int n_freq, double freq_log_step,
                            int em_flag, int s_max, int s_input_on, double *tb, double *vi)
 {
-    RT_TRY(use(c));
+    RT_USE(c);
     if (c->smp_n <= 0 || c->smp_rays <= 0) return fail(RTGRFF_EINVAL, "no samples on the device (call rtgrff_sample_traced)");
     if (n_freq <= 0 || !tb || !vi) return fail(RTGRFF_EINVAL, "bad n_freq / null output");
     const size_t n = (size_t)c->smp_rays * n_freq;
@@ -668,7 +1070,7 @@ int rtgrff_render_map(rtgrff_ctx *c, int64_t n_rays, const double *x_start, cons
                       int use_bvec, int voxel_order, int s_mode, int s_input_on, double *tb, double *vi, int out_on_device,
                       int64_t *stats)
 {
-    RT_TRY(use(c));
+    RT_USE(c);
     if (!c->has_wcube) return fail(RTGRFF_ENOCUBE, "rtgrff_set_omega_cube has not been called");
     if (!c->has_fcube) return fail(RTGRFF_ENOCUBE, "rtgrff_set_field_cubes has not been called");
     if (use_bvec && !c->has_bvec) return fail(RTGRFF_ENOCUBE, "use_bvec needs bx,by,bz in rtgrff_set_field_cubes");
@@ -703,6 +1105,15 @@ int rtgrff_render_map(rtgrff_ctx *c, int64_t n_rays, const double *x_start, cons
     if (kvec) RT_TRY(h2d(c, c->in3, kvec, 3 * nb));
     if (ray_order) {
         if (n_rays >= ((int64_t)1 << 31)) return fail(RTGRFF_EINVAL, "ray_order needs n_rays < 2^31");
+        // the kernel reads x_start[ray_order[t]] and writes tb[ray_order[t]]: anything but a permutation of
+        // 0..n_rays-1 would read / write out of bounds or leave pixels unwritten
+        std::vector<uint8_t> seen((size_t)n_rays, 0);
+        for (int64_t t = 0; t < n_rays; ++t) {
+            const int32_t r = ray_order[t];
+            if (r < 0 || r >= n_rays || seen[(size_t)r])
+                return fail(RTGRFF_EINVAL, "ray_order is not a permutation of 0..n_rays-1 (entry %lld = %d)", (long long)t, r);
+            seen[(size_t)r] = 1;
+        }
         RT_TRY(h2d(c, c->out2, ray_order, (size_t)n_rays * sizeof(int32_t)));
     }
     RT_TRY(c->counters.reserve(64));
@@ -782,10 +1193,119 @@ int rtgrff_render_map(rtgrff_ctx *c, int64_t n_rays, const double *x_start, cons
     return RTGRFF_OK;
 }
 
+// ---- multi-GPU: row sharding + image gather ---------------------------------------------------------
+int rtgrff_shard_rows(int n_rows, int world_size, int rank, int32_t *rows, int *n_local, int *max_rows)
+{
+    if (n_rows < 0 || world_size < 1 || rank < 0 || rank >= world_size) return fail(RTGRFF_EINVAL, "bad n_rows / world_size / rank");
+    const int G = row_group_of(n_rows, world_size);
+    int n = 0;
+    for (int row = 0; row < n_rows; ++row)
+        if ((row / G) % world_size == rank) {
+            if (rows) rows[n] = row;
+            ++n;
+        }
+    if (n_local) *n_local = n;
+    if (max_rows) *max_rows = max_rows_per_rank(n_rows, world_size);
+    return RTGRFF_OK;
+}
+
+int rtgrff_comm_unique_id(char id[128])
+{
+    if (!id) return fail(RTGRFF_EINVAL, "null id");
+    NcclApi *n = nccl_api();
+    if (!n) return fail(RTGRFF_EUNSUPPORTED, "libnccl.so.2 could not be loaded (%s)", dlerror() ? "dlopen failed" : "symbols missing");
+    NcclUniqueId u;
+    const int rc = n->GetUniqueId(&u);
+    if (rc != 0) return fail(RTGRFF_ECUDA, "ncclGetUniqueId -> %s", n->GetErrorString(rc));
+    memcpy(id, u.internal, 128);
+    return RTGRFF_OK;
+}
+
+int rtgrff_comm_init_rank(rtgrff_ctx *c, int world_size, int rank, const char id[128])
+{
+    RT_USE(c);
+    if (world_size < 1 || rank < 0 || rank >= world_size) return fail(RTGRFF_EINVAL, "bad world_size / rank");
+    if (c->comm) return fail(RTGRFF_EINVAL, "the context already has a communicator");
+    c->comm_rank = rank; c->comm_size = world_size;
+    if (world_size == 1) return RTGRFF_OK;        // nothing to talk to
+    if (!id) return fail(RTGRFF_EINVAL, "null id");
+    NcclApi *n = nccl_api();
+    if (!n) return fail(RTGRFF_EUNSUPPORTED, "libnccl.so.2 could not be loaded");
+    NcclUniqueId u;
+    memcpy(u.internal, id, 128);
+    NcclComm comm = nullptr;
+    const int rc = n->CommInitRank(&comm, world_size, u, rank);
+    if (rc != 0) return fail(RTGRFF_ECUDA, "ncclCommInitRank -> %s", n->GetErrorString(rc));
+    c->comm = comm;
+    return RTGRFF_OK;
+}
+
+int rtgrff_comm_destroy(rtgrff_ctx *c)
+{
+    RT_USE(c);
+    if (c->comm) {
+        NcclApi *n = nccl_api();
+        cudaStreamSynchronize(c->stream);
+        if (n) n->CommDestroy((NcclComm)c->comm);
+        c->comm = nullptr;
+    }
+    c->comm_rank = 0; c->comm_size = 1;
+    return RTGRFF_OK;
+}
+
+int rtgrff_gather_image(rtgrff_ctx *c, const double *slab, int n_planes, int n_rows, int n_cols, int root, double *image,
+                        int image_on_device)
+{
+    RT_USE(c);
+    const int W = c->comm_size, me = c->comm_rank;
+    if (!slab || n_planes < 1 || n_rows < 1 || n_cols < 1 || root < 0 || root >= W) return fail(RTGRFF_EINVAL, "bad arguments");
+    if (me == root && !image) return fail(RTGRFF_EINVAL, "the root needs an image buffer");
+    if (W > 1 && !c->comm) return fail(RTGRFF_EINVAL, "rtgrff_comm_init_rank has not been called");
+    const int mr = max_rows_per_rank(n_rows, W), G = row_group_of(n_rows, W);
+    const size_t slab_n = (size_t)n_planes * mr * n_cols, img_n = (size_t)n_planes * n_rows * n_cols;
+    const double *gathered = slab;
+    RT_CUDA(cudaEventRecord(c->ev0, c->stream));
+    if (W > 1) {
+        NcclApi *n = nccl_api();
+        int rc = n->GroupStart();
+        if (me == root) {
+            RT_TRY(c->gather_buf.reserve((size_t)W * slab_n * sizeof(double)));
+            double *buf = c->gather_buf.as<double>();
+            for (int r = 0; r < W && rc == 0; ++r) {
+                if (r == me) continue;
+                rc = n->Recv(buf + (size_t)r * slab_n, slab_n * sizeof(double), kNcclInt8, r, (NcclComm)c->comm, c->stream);
+            }
+            gathered = buf;
+        } else if (rc == 0) {
+            rc = n->Send(slab, slab_n * sizeof(double), kNcclInt8, root, (NcclComm)c->comm, c->stream);
+        }
+        const int rc2 = n->GroupEnd();
+        if (rc != 0 || rc2 != 0) return fail(RTGRFF_ECUDA, "NCCL gather -> %s", n->GetErrorString(rc ? rc : rc2));
+        if (me == root)
+            RT_CUDA(cudaMemcpyAsync(c->gather_buf.as<double>() + (size_t)me * slab_n, slab, slab_n * sizeof(double),
+                                    cudaMemcpyDeviceToDevice, c->stream));
+    }
+    if (me == root) {
+        double *dimg = image;
+        if (!image_on_device) {
+            RT_TRY(c->image_buf.reserve(img_n * sizeof(double)));
+            dimg = c->image_buf.as<double>();
+        }
+        const unsigned int blocks = (unsigned int)std::min<int64_t>(blocks_for((int64_t)img_n, 256), (int64_t)c->sm_count * 16);
+        place_rows_kernel<<<blocks, 256, 0, c->stream>>>(gathered, dimg, n_planes, n_rows, n_cols, mr, W, G);
+        RT_TRY(launched(c, "place_rows_kernel"));
+        RT_CUDA(cudaEventRecord(c->ev1, c->stream));
+        c->ev_valid = true;
+        if (!image_on_device) return d2h_large(c, image, dimg, img_n * sizeof(double));
+    }
+    RT_CUDA(cudaStreamSynchronize(c->stream));
+    return RTGRFF_OK;
+}
+
 int rtgrff_gaussian_beam(rtgrff_ctx *c, const double *img, int ny, int nx, int n_planes, double sigma_pix,
                          double truncate, double *out)
 {
-    RT_TRY(use(c));
+    RT_USE(c);
     if (!img || !out || ny < 1 || nx < 1 || n_planes < 1) return fail(RTGRFF_EINVAL, "bad arguments");
     if (!(sigma_pix >= 0.0) || !isfinite(sigma_pix) || !(truncate > 0.0)) return fail(RTGRFF_EINVAL, "bad sigma/truncate");
     const size_t n = (size_t)n_planes * ny * nx, nb = n * sizeof(double);
@@ -818,7 +1338,7 @@ int rtgrff_gaussian_beam(rtgrff_ctx *c, const double *img, int ny, int nx, int n
 
 int rtgrff_patch_nan(rtgrff_ctx *c, double *img, int ny, int nx, int n_planes, int max_passes, int64_t *n_patched)
 {
-    RT_TRY(use(c));
+    RT_USE(c);
     if (!img || ny < 1 || nx < 1 || n_planes < 1 || max_passes < 0) return fail(RTGRFF_EINVAL, "bad arguments");
     if (n_patched) *n_patched = 0;
     const size_t n = (size_t)n_planes * ny * nx, nb = n * sizeof(double);

@@ -81,7 +81,7 @@ def resample_to_xyz_cube(model, var_name, x_grid, y_grid, z_grid, phi0_offset=0.
                          r_min=R_MIN, context=None):
     """Resample one model variable onto a regular xyz grid (build_rays.py:69-70); returns float64
     (nx, ny, nz) in the variable's physical unit."""
-    ctx = context or _lib.default_context(0)
+    ctx = context or _lib.default_context()
     slot = SLOTS.get(var_name, 0)
     return _resample(ctx, slot, model[var_name], x_grid, y_grid, z_grid, phi0_offset, fill_nan, r_min, True)
 

@@ -41,6 +41,39 @@ def shard_rays(N_pix_x: int, N_pix_y: int, world_size: int, rank: int):
     return (rows[:, None] * N_pix_x + np.arange(N_pix_x)[None, :]).ravel(), rows
 
 
+def c_shard_rows(n_rows: int, world_size: int, rank: int):
+    """The same partition from the C ABI (rtgrff_shard_rows), which is what a non-Python host calls and what
+    rtgrff_gather_image assumes: (rows, max_rows_per_rank)."""
+    import ctypes
+    from . import _lib
+    lib = _lib.load()
+    rows = np.empty(max(n_rows, 1), dtype=np.int32)
+    n_local, max_rows = ctypes.c_int(0), ctypes.c_int(0)
+    _lib.check(lib.rtgrff_shard_rows(int(n_rows), int(world_size), int(rank), _lib.ptr(rows, ctypes.c_int32),
+                                     ctypes.byref(n_local), ctypes.byref(max_rows)))
+    return rows[:n_local.value].astype(np.int64), int(max_rows.value)
+
+
+def init_comm(session, group=None):
+    """NCCL communicator of the library over all ranks of the torch.distributed group (any backend):
+    rank 0 draws the unique id (rtgrff_comm_unique_id), torch.distributed carries its 128 bytes to
+    the others, every rank joins (rtgrff_comm_init_rank).  The image then travels through
+    ``RaySession.gather_image`` (rtgrff_gather_image), not through torch."""
+    import ctypes
+    import torch.distributed as dist
+    from . import _lib
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    box = [None]
+    if rank == 0 and world > 1:
+        buf = ctypes.create_string_buffer(128)
+        _lib.check(_lib.load().rtgrff_comm_unique_id(buf))
+        box[0] = buf.raw
+    if world > 1:
+        dist.broadcast_object_list(box, src=0, group=group)
+    session.comm_init(world, rank, box[0])
+    return world, rank
+
+
 def gather_rows(local, n_rows: int, group=None):
     """All-gather per-rank slabs ``local`` of shape (..., max_rows_per_rank, N_x) (rows beyond the
     rank's share are padding) into the full (..., n_rows, N_x) image on every rank.  `local` is a

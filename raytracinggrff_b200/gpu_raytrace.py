@@ -38,7 +38,7 @@ def _device(device: str) -> str:
 
 
 def _session():
-    return RaySession(context=_lib.default_context(0))
+    return RaySession(context=_lib.default_context())
 
 
 def trace_ray(device, omega_pe_3d, x_grid, y_grid, z_grid, freq_hz, x_start, y_start, z_start, kvec_in_norm,
@@ -48,7 +48,7 @@ def trace_ray(device, omega_pe_3d, x_grid, y_grid, z_grid, freq_hz, x_start, y_s
     arrays (empty list when cross-sections are not traced)."""
     _device(device)
     ses = _session()
-    ses.set_omega_cube(omega_pe_3d, x_grid, y_grid, z_grid)
+    ses.set_omega_cube(omega_pe_3d, x_grid, y_grid, z_grid, reuse=True)   # same arrays as last call: already there
     mode = {"per_step": _lib.S_PER_STEP, "cumulative": _lib.S_CUMULATIVE}[s_mode]
     r_record, s_record, _ = ses.trace(freq_hz, x_start, y_start, z_start, kvec_in_norm, dt, n_steps,
                                       record_stride, trace_crosssections, perturb_ratio, mode)
@@ -63,7 +63,7 @@ def sample_model_with_rays(device, x_grid, y_grid, z_grid, ne_xyz, te_xyz, b_xyz
     (n_steps, n_rays) (float32 x5, bool), exactly the reference's dict (gpu_raytrace.py:651)."""
     _device(device)
     ses = _session()
-    ses.set_field_cubes(x_grid, y_grid, z_grid, ne_xyz, te_xyz, b_xyz)
+    ses.set_field_cubes(x_grid, y_grid, z_grid, ne_xyz, te_xyz, b_xyz, reuse=True)
     return ses.sample(r_record, s_arr, ray_start, r_sun_cm, fill_ne, fill_te, fill_b)
 
 

@@ -32,18 +32,18 @@ def initGET_MW(libname=None):
     return mwfunc
 
 
-def _host(a):
-    if hasattr(a, "get") and not isinstance(a, np.ndarray):   # CuPy-like array
-        return a.get()
-    return np.asarray(a)
-
-
 def get_mw_slice(Lparms_M, Rparms_M, Parms_M, T_arr, DEM_arr, DDM_arr, RL_M, tile_pixels=None, heap_bytes=None,
                  session=None):
     """fastGRFF.get_mw_slice contract: Lparms_M int32[6] {Npix,Nz,Nf,NT,DEMkey,DDMkey},
-    Rparms_M (3,Npix), Parms_M (15,Nz,Npix), RL_M (7,Nf,Npix), all Fortran order."""
-    ses = session or RaySession(context=_lib.default_context(0))
-    L = _host(Lparms_M)
-    if not isinstance(RL_M, np.ndarray):
-        raise TypeError("RL_M must be a numpy array (written in place)")
-    return ses.get_mw_slice(L, _host(Rparms_M), _host(Parms_M), RL_M)
+    Rparms_M (3,Npix), Parms_M (15,Nz,Npix), RL_M (7,Nf,Npix), all Fortran order.
+
+    The reference calls it with CuPy arrays and reads ``RL_M`` back from the device afterwards
+    (script/resample_with_ray_tracing.py:428-452): any array exposing ``__cuda_array_interface__``
+    (CuPy, torch, numba) is used where it is and ``RL_M`` is written in place on the device.  With
+    numpy arrays the library stages them itself and writes the numpy ``RL_M`` in place.  Returns the
+    per-pixel status as a numpy int32 array (0 = ok), which is what the call site tests."""
+    ses = session or RaySession(context=_lib.default_context())
+    if _lib.cuda_array(RL_M) is None and not isinstance(RL_M, np.ndarray):
+        raise TypeError("RL_M must be a numpy array or a device array exposing __cuda_array_interface__ "
+                        "(it is written in place)")
+    return ses.get_mw_slice(Lparms_M, Rparms_M, Parms_M, RL_M)

@@ -62,7 +62,7 @@ def resample_MAS(model, N_pix, X_range, Y_range, N_z, dz0, variable_spacing_z=Tr
     for k in ("br", "bt", "bp"):
         if k not in model:
             raise ValueError("Magnetic field components (br, bt, bp) not all found!")
-    ctx = context or _lib.default_context(0)
+    ctx = context or _lib.default_context()
     zc, dz = z_grid(N_z, dz0, variable_spacing_z, z_range)
     xs = np.linspace(X_range[0], X_range[1], N_pix)
     ys = np.linspace(Y_range[0], Y_range[1], N_pix)
@@ -108,7 +108,7 @@ def SyntheticFF(fname_input, freq0, Nfreq, freq_log_step, fname_output=None, do_
     R = np.zeros((3, npix), dtype=np.float64, order="F")
     R[0], R[1], R[2] = area, freq0, freq_log_step
     RL = np.zeros((7, Nf, npix), dtype=np.float64, order="F")
-    ses = session or RaySession(context=_lib.default_context(0))
+    ses = session or RaySession(context=_lib.default_context())
     status = ses.get_mw_slice(L, R, P, RL)
     inten = (RL[5] + RL[6]).T                                                    # (npix, Nf), :212
     with np.errstate(invalid="ignore", divide="ignore"):

@@ -24,12 +24,35 @@ def _s_mode(v):
     return int(v)
 
 
+def _fingerprint(*arrays):
+    """Identity + sampled content of host arrays: address, shape, dtype, strides and a hash of ~4096
+    evenly spaced elements each.  Used to skip the re-upload of a cube the device already holds when the
+    drop-in functions are called again with the same arrays (the reference re-uploads per call,
+    gpu_raytrace.py:354, :681).  RTGRFF_CUBE_CACHE=0 turns the shortcut off."""
+    import os
+    if os.environ.get("RTGRFF_CUBE_CACHE", "1") == "0":
+        return None
+    key = []
+    for a in arrays:
+        if a is None:
+            key.append(None)
+            continue
+        a = np.asarray(a)
+        flat = a.reshape(-1) if a.flags.c_contiguous else a.ravel()
+        step = max(1, flat.size // 4096)
+        key.append((a.__array_interface__["data"][0], a.shape, a.dtype.str, a.strides,
+                    hash(flat[::step].tobytes()), hash(flat[-1:].tobytes())))
+    return tuple(key)
+
+
 class RaySession:
-    def __init__(self, device=0, stream=None, context=None):
+    def __init__(self, device=None, stream=None, context=None):
         self.ctx = context if context is not None else _lib.Context(device, stream)
         self._lib = _lib.load()
         self.n_rec = 0
         self.n_rays = 0
+        self.cube_shape = None
+        self.world_size, self.rank = 1, 0
         self.traced_cs = False
 
     def close(self):
@@ -42,18 +65,32 @@ class RaySession:
         self.close()
 
     # -- cubes ---------------------------------------------------------------------------------
-    def set_omega_cube(self, omega_pe_3d, x_grid, y_grid, z_grid):
-        """build_rays.py:132-143 / gpu_raytrace.py:346-357."""
+    def set_omega_cube(self, omega_pe_3d, x_grid, y_grid, z_grid, reuse=False):
+        """build_rays.py:132-143 / gpu_raytrace.py:346-357.  reuse=True: skip the upload when the context
+        already holds the cube built from these very arrays (see _fingerprint)."""
         geom = _lib.grid_geom(x_grid, y_grid, z_grid)
+        keys = self.ctx.__dict__.setdefault("_cube_keys", {})
+        key = _fingerprint(omega_pe_3d, x_grid, y_grid, z_grid) if reuse else None
+        if key is not None and keys.get("omega") == key:
+            self.cube_shape = tuple(np.shape(omega_pe_3d))
+            return
+        keys["omega"] = None
         w = f64(omega_pe_3d)
         if w.ndim != 3 or w.shape != (len(x_grid), len(y_grid), len(z_grid)):
             raise ValueError(f"omega_pe_3d shape {w.shape} does not match the grids")
         check(self._lib.rtgrff_set_omega_cube(self.ctx.handle, w.ctypes.data_as(ctypes.c_void_p), *w.shape,
                                               ptr(geom, c_double), 0))
+        self.cube_shape = tuple(w.shape)
+        keys["omega"] = key
 
-    def set_field_cubes(self, x_grid, y_grid, z_grid, ne_xyz, te_xyz, b_xyz, bx=None, by=None, bz=None):
+    def set_field_cubes(self, x_grid, y_grid, z_grid, ne_xyz, te_xyz, b_xyz, bx=None, by=None, bz=None, reuse=False):
         """gpu_raytrace.py:638-649 (_as_float32_c of each field, uniform-grid check)."""
         geom = _lib.grid_geom(x_grid, y_grid, z_grid)
+        keys = self.ctx.__dict__.setdefault("_cube_keys", {})
+        key = _fingerprint(ne_xyz, te_xyz, b_xyz, bx, by, bz, x_grid, y_grid, z_grid) if reuse else None
+        if key is not None and keys.get("fields") == key:
+            return
+        keys["fields"] = None
         ne, te, b = f32(ne_xyz), f32(te_xyz), f32(b_xyz)
         shape = (len(x_grid), len(y_grid), len(z_grid))
         for name, a in (("ne_xyz", ne), ("te_xyz", te), ("b_xyz", b)):
@@ -70,12 +107,15 @@ class RaySession:
         check(self._lib.rtgrff_set_field_cubes(self.ctx.handle, ptr(ne, c_float), ptr(te, c_float), ptr(b, c_float),
                                                ptr(vec[0], c_float), ptr(vec[1], c_float), ptr(vec[2], c_float),
                                                *shape, ptr(geom, c_double)))
+        keys["fields"] = key
 
     def set_model_from_spherical(self, model, x_grid, y_grid, z_grid, phi0_offset=0.0, want_bvec=False):
         """Cubes straight from a spherical (phi, latitude, r) model, never visiting the host
         (cubes.set_model_from_spherical; script/resample_with_ray_tracing.py:263-293)."""
         from . import cubes
+        self.ctx.__dict__["_cube_keys"] = {}
         cubes.set_model_from_spherical(self, model, x_grid, y_grid, z_grid, phi0_offset, want_bvec)
+        self.cube_shape = (len(x_grid), len(y_grid), len(z_grid))
 
     # -- integrator ----------------------------------------------------------------------------
     def trace(self, freq_hz, x_start, y_start, z_start, kvec_in_norm, dt, n_steps, record_stride=10,
@@ -124,7 +164,7 @@ class RaySession:
                                       ptr(rs, c_float), float(r_sun_cm), float(fill_ne), float(fill_te), float(fill_b),
                                       ptr(out["ne"], c_float), ptr(out["te"], c_float), ptr(out["b"], c_float),
                                       ptr(out["ds"], c_float), ptr(valid, c_uint8)))
-        out["valid_mask"] = valid.astype(bool)
+        out["valid_mask"] = valid.view(np.bool_)      # 0/1 bytes: no copy
         out["s"] = s
         return out
 
@@ -145,14 +185,20 @@ class RaySession:
                                              ptr(out.get("ds"), c_float), ptr(valid, c_uint8),
                                              ptr(out.get("s"), c_float)))
         if fetch:
-            out["valid_mask"] = valid.astype(bool)
+            out["valid_mask"] = valid.view(np.bool_)      # 0/1 bytes: no copy
         return out
 
     # -- GRFF ----------------------------------------------------------------------------------
     def get_mw_slice(self, Lparms_M, Rparms_M, Parms_M, RL_M):
         """fastGRFF get_mw_slice contract (script/resample_with_ray_tracing.py:428-446); RL_M written
-        in place (must be Fortran-ordered float64 (7,Nf,Npix)); returns status int32 (Npix)."""
-        L = np.asfortranarray(Lparms_M, dtype=np.int32)
+        in place (must be Fortran-ordered float64 (7,Nf,Npix)); returns status int32 (Npix).
+        With device arrays (anything exposing ``__cuda_array_interface__``: the reference passes CuPy
+        arrays) for Rparms_M / Parms_M / RL_M the call runs on them where they are and RL_M is written in
+        place on the device; host numpy arrays are staged through the library."""
+        dev = [_lib.cuda_array(a) for a in (Rparms_M, Parms_M, RL_M)]
+        if any(d is not None for d in dev):
+            return self._get_mw_slice_device(Lparms_M, dev, (Rparms_M, Parms_M, RL_M))
+        L = self._host_ints(Lparms_M, 6)
         R = np.asfortranarray(Rparms_M, dtype=np.float64)
         P = np.asfortranarray(Parms_M, dtype=np.float64)
         npix, nz, nf = int(L[0]), int(L[1]), int(L[2])
@@ -165,6 +211,110 @@ class RaySession:
         check(self._lib.rtgrff_get_mw_slice(self.ctx.handle, ptr(L, ctypes.c_int32), ptr(R, c_double), ptr(P, c_double),
                                             None, None, None, ptr(RL_M, c_double), ptr(status, ctypes.c_int32)))
         return status
+
+    def _host_ints(self, a, n):
+        """n int32 values of a host or device array (Lparms_M is a CuPy array at the reference's call site)."""
+        d = _lib.cuda_array(a)
+        if d is None:
+            return np.asarray(a, dtype=np.int32).ravel()[:n].copy()
+        p, shape, typestr, _ = d
+        if np.dtype(typestr) != np.int32 or int(np.prod(shape)) < n:
+            raise ValueError("Lparms_M must hold at least 6 int32 values")
+        out = np.empty(n, dtype=np.int32)
+        check(self._lib.rtgrff_memcpy(self.ctx.handle, out.ctypes.data_as(ctypes.c_void_p), ctypes.c_void_p(p), 4 * n, 1))
+        return out
+
+    def _get_mw_slice_device(self, Lparms_M, dev, arrays):
+        L = self._host_ints(Lparms_M, 6)
+        npix, nz, nf = int(L[0]), int(L[1]), int(L[2])
+        want = ((3, npix), (15, nz, npix), (7, nf, npix))
+        ptrs, keep = [], []
+        for name, d, a, shape in zip(("Rparms_M", "Parms_M", "RL_M"), dev, arrays, want):
+            if d is None:
+                if name == "RL_M":
+                    raise TypeError("RL_M must be a device array when Rparms_M / Parms_M are (it is written in place)")
+                # a host array next to device ones: stage it on the device for the call
+                h = np.asfortranarray(a, dtype=np.float64)
+                if h.shape != shape:
+                    raise ValueError(f"{name} must have shape {shape}")
+                buf = self._device_scratch(name, h.nbytes)
+                check(self._lib.rtgrff_memcpy(self.ctx.handle, ctypes.c_void_p(buf), h.ctypes.data_as(ctypes.c_void_p), h.nbytes, 0))
+                ptrs.append(buf)
+                continue
+            p, shp, typestr, strides = d
+            if np.dtype(typestr) != np.float64 or tuple(shp) != shape:
+                raise ValueError(f"{name} must be float64 with shape {shape}, got {typestr} {tuple(shp)}")
+            if not _lib.is_f_contiguous(shp, strides, 8):
+                raise ValueError(f"{name} must be Fortran-ordered (order='F'), as the reference builds it")
+            ptrs.append(p)
+            keep.append(a)
+        status_dev = self._device_scratch("status", 4 * max(npix, 1))
+        Lh = np.ascontiguousarray(L, dtype=np.int32)
+        check(self._lib.rtgrff_get_mw_slice_device(self.ctx.handle, ptr(Lh, ctypes.c_int32), ctypes.c_void_p(ptrs[0]),
+                                                   ctypes.c_void_p(ptrs[1]), ctypes.c_void_p(ptrs[2]),
+                                                   ctypes.c_void_p(status_dev)))
+        status = np.zeros(npix, dtype=np.int32)
+        if npix:
+            check(self._lib.rtgrff_memcpy(self.ctx.handle, status.ctypes.data_as(ctypes.c_void_p),
+                                          ctypes.c_void_p(status_dev), 4 * npix, 1))
+        return status
+
+    def _device_scratch(self, key, nbytes):
+        """Device scratch buffers owned by this session (rtgrff_device_alloc), grown on demand."""
+        cache = self.__dict__.setdefault("_scratch", {})
+        ent = cache.get(key)
+        if ent is None or ent[1] < nbytes:
+            p = ctypes.c_void_p()
+            check(self._lib.rtgrff_device_alloc(self.ctx.handle, ctypes.byref(p), int(nbytes)))
+            if ent is not None:
+                self._lib.rtgrff_device_free(self.ctx.handle, ctypes.c_void_p(ent[0]))
+            ent = cache[key] = (p.value, int(nbytes))
+        return ent[0]
+
+    def export_cubes(self, omega_pe=True, fields=True, bvec=False):
+        """Host copies of the device cubes (rtgrff_export_cubes): the float64 omega_pe exactly as it was
+        differenced, n_e / T / |B| and the B vector as stored.  For parity checks of cubes built on the
+        device from a spherical model against a CPU implementation."""
+        shape = self.cube_shape
+        out = {}
+        if omega_pe:
+            out["omega_pe"] = np.empty(shape, dtype=np.float64)
+        if fields:
+            for k in ("ne", "te", "b"):
+                out[k] = np.empty(shape, dtype=np.float32)
+        if bvec:
+            for k in ("bx", "by", "bz"):
+                out[k] = np.empty(shape, dtype=np.float32)
+        check(self._lib.rtgrff_export_cubes(self.ctx.handle, ptr(out.get("omega_pe"), c_double), ptr(out.get("ne"), c_float),
+                                            ptr(out.get("te"), c_float), ptr(out.get("b"), c_float),
+                                            ptr(out.get("bx"), c_float), ptr(out.get("by"), c_float),
+                                            ptr(out.get("bz"), c_float)))
+        return out
+
+    # -- multi-GPU -----------------------------------------------------------------------------
+    def comm_init(self, world_size, rank, unique_id=None):
+        """rtgrff_comm_init_rank: NCCL communicator over the sessions of all ranks (collective)."""
+        check(self._lib.rtgrff_comm_init_rank(self.ctx.handle, int(world_size), int(rank), unique_id))
+        self.world_size, self.rank = int(world_size), int(rank)
+
+    def comm_destroy(self):
+        check(self._lib.rtgrff_comm_destroy(self.ctx.handle))
+
+    def gather_image(self, slab_ptr, n_planes, n_rows, n_cols, root=0, out=None, out_device_ptr=None):
+        """rtgrff_gather_image: the ranks' slabs (device float64 (n_planes, max_rows, n_cols)) -> the image
+        (n_planes, n_rows, n_cols) on `root`: into `out` (host float64 array, page-locked memory is
+        written by DMA directly) or to the device pointer `out_device_ptr`.  Returns `out` on the root."""
+        if out_device_ptr is not None:
+            dst, on_dev = ctypes.c_void_p(int(out_device_ptr)), 1
+        elif out is not None:
+            if out.dtype != np.float64 or not out.flags.c_contiguous or out.size != n_planes * n_rows * n_cols:
+                raise ValueError("out must be a C-contiguous float64 array of n_planes*n_rows*n_cols elements")
+            dst, on_dev = out.ctypes.data_as(ctypes.c_void_p), 0
+        else:
+            dst, on_dev = None, 0
+        check(self._lib.rtgrff_gather_image(self.ctx.handle, ctypes.c_void_p(int(slab_ptr)), int(n_planes), int(n_rows),
+                                            int(n_cols), int(root), dst, on_dev))
+        return out
 
     def emission_traced(self, pixel_area_cm2, freq0, n_freq=1, freq_log_step=0.0, em_flag=5, s_max=30,
                         s_input_on=False):

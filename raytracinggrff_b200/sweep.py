@@ -85,7 +85,7 @@ def tb_spectra(model, out_dir, N_pix=128, fmin_mhz=30.0, fmax_mhz=800.0, n_freq=
     freqs_hz = np.logspace(np.log10(fmin_mhz), np.log10(fmax_mhz), n_freq) * 1e6
     if start_from_idx < 0 or start_from_idx >= len(freqs_hz):
         raise ValueError(f"--start-from-idx must be in [0, {len(freqs_hz)-1}]")
-    ses = session or RaySession(0)
+    ses = session or RaySession()
     rows = []
     for i, freq_hz in enumerate(freqs_hz):
         tag = f"{i:02d}_{freq_hz/1e6:08.3f}MHz"

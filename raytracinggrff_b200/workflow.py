@@ -97,7 +97,7 @@ def run_ray_tracing_emission(model, N_pix=64, X_fov=1.44, freq_hz=75e6, z_observ
     # meaning of that slot to a private GRFF build; here the voxel's source term is multiplied by
     # Parms[14] / area = S (include/rtgrff.h).  s_mode picks the S of the reference's CPU path (per step,
     # ~1) or of its CUDA path (cumulative since the start of the ray: the pencil's magnification).
-    ses = session or RaySession(context=_lib.default_context(0))
+    ses = session or RaySession(context=_lib.default_context())
     if "omega_pe" in model:
         xg, yg, zg = model["x_grid"], model["y_grid"], model["z_grid"]
         ses.set_omega_cube(model["omega_pe"], xg, yg, zg)

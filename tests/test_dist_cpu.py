@@ -86,3 +86,18 @@ def test_row_sharding_is_a_partition_for_any_size():
             assert np.all(np.diff(rows[r]) > 0)
             idx, rr = rdist.shard_rays(7, n_rows, world, r)
             assert np.array_equal(rr, rows[r]) and idx.size == 7 * len(rows[r])
+
+
+def test_c_abi_row_sharding_equals_the_python_partition():
+    """rtgrff_shard_rows (host-only entry of the C ABI: what a non-Python host calls and what
+    rtgrff_gather_image assumes) against dist.rows_of_rank for every world size the bench uses."""
+    from raytracinggrff_b200 import dist as rdist
+    for world in (1, 2, 3, 4, 8):
+        for n in (1, 7, 64, 129, 512, 2048):
+            seen = []
+            for r in range(world):
+                rows, mr = rdist.c_shard_rows(n, world, r)
+                assert np.array_equal(rows, rdist.rows_of_rank(n, world, r))
+                assert mr == rdist.max_rows_per_rank(n, world)
+                seen.append(rows)
+            assert np.array_equal(np.sort(np.concatenate(seen)), np.arange(n))
