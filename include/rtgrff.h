@@ -49,6 +49,10 @@ int rtgrff_ctx_create_on_stream(int device, void *stream, rtgrff_ctx **out);
 int rtgrff_current_device(void);
 int rtgrff_ctx_destroy(rtgrff_ctx *ctx);
 int rtgrff_ctx_synchronize(rtgrff_ctx *ctx);
+/* Large host arrays travel in chunks through page-locked bounce buffers, overlapped with the kernels
+ * (rtgrff_sample, rtgrff_get_mw_slice, cube uploads, image download).  enabled = 0 switches to one plain copy
+ * each way, so that rtgrff_ctx_last_kernel_ms brackets the kernel alone (default 1; env RTGRFF_PIPELINE=0). */
+int rtgrff_ctx_set_pipeline(rtgrff_ctx *ctx, int enabled);
 /* Kernel launches issued by this context since creation (for bench.py's gpu_launches). */
 int64_t rtgrff_ctx_launch_count(const rtgrff_ctx *ctx);
 /* Device time in ms of the dominant kernel of the last trace/sample/get_mw_slice/emission/render

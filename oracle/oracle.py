@@ -122,9 +122,12 @@ def gradient(f, h, axis):
 
 def ray_trace(omega_pe_3d, x_grid, y_grid, z_grid, freq_hz, x_start, y_start, z_start,
               kvec_in_norm, dt, n_steps, record_stride=10, trace_crosssections=False,
-              cross_section_stride=1, perturb_ratio=2, n_threads=0, return_active=False):
+              cross_section_stride=1, perturb_ratio=2, n_threads=0, return_active=False, cache_gradient=False):
     """Same signature and return convention as build_rays.ray_trace (build_rays.py:128-130, :248):
-    (r_record float64 (n_rec,n_rays,3), list of n_rec float64 (n_rays,) arrays or [])."""
+    (r_record float64 (n_rec,n_rays,3), list of n_rec float64 (n_rays,) arrays or []).
+    cache_gradient: keep np.gradient(omega_pe) between calls on the same cube array (the benchmark's
+    sub-sampled CPU legs: over a full map that preparation is amortised over millions of rays; the caller
+    must not modify the array in between)."""
     w = _f64(omega_pe_3d)
     xg, yg, zg = _f64(x_grid), _f64(y_grid), _f64(z_grid)
     xs, ys, zs = _f64(x_start), _f64(y_start), _f64(z_start)
@@ -139,7 +142,8 @@ def ray_trace(omega_pe_3d, x_grid, y_grid, z_grid, freq_hz, x_start, y_start, z_
     rc = _lib().oracle_ray_trace(_p(w, d), _p(xg, d), _p(yg, d), _p(zg, d), *w.shape, float(freq_hz),
                                  _p(xs, d), _p(ys, d), _p(zs, d), _p(kv, d), n_rays, float(dt), n_steps,
                                  stride, int(bool(trace_crosssections)), float(perturb_ratio),
-                                 int(n_threads), _p(r_record, d), _p(s_record, d), ctypes.byref(active))
+                                 int(n_threads) if not cache_gradient else -1 - int(n_threads),
+                                 _p(r_record, d), _p(s_record, d), ctypes.byref(active))
     if rc != 0:
         raise MemoryError("oracle_ray_trace allocation failed")
     cs = [s_record[i].copy() for i in range(n_rec)] if trace_crosssections else []
@@ -285,7 +289,7 @@ def emission_from_samples(sampled, N_pix, X_fov, freq0, Nfreq=1, freq_log_step=0
 
 
 def chain_bvec(cube, freq_hz, dt, n_steps, record_stride, xs, ys, zs, area, em_flag=4, s_max=30, perturb_ratio=2,
-               n_threads=0, ray_chunk=128, return_paths=False):
+               n_threads=0, ray_chunk=128, return_paths=False, cache_gradient=False):
     """The reference chain for a GR+FF map with the angle to B taken along the ray — the physics the fused
     kernel is benchmarked on (BASELINE configs 4 and 5), restated with the reference's own stages:
       ray_trace (build_rays.py:128-248, cross-sections on)
@@ -301,7 +305,7 @@ def chain_bvec(cube, freq_hz, dt, n_steps, record_stride, xs, ys, zs, area, em_f
     ray_start = np.column_stack([xs, ys, zs])
     g3 = (cube["x_grid"], cube["y_grid"], cube["z_grid"])
     r, cs = ray_trace(cube["omega_pe"], *g3, freq_hz, xs, ys, zs, kv, dt, n_steps, record_stride, True,
-                      perturb_ratio=perturb_ratio, n_threads=n_threads)
+                      perturb_ratio=perturb_ratio, n_threads=n_threads, cache_gradient=cache_gradient)
     s_rec = np.array(cs)
     smp = sample_model_with_rays_cpu(*g3, cube["ne"], cube["te"], cube["b"], r, s_rec, ray_start, R_SUN_CM)
     bv = sample_model_with_rays_cpu(*g3, cube["bx"], cube["by"], cube["bz"], r, s_rec, ray_start, R_SUN_CM,

@@ -45,10 +45,15 @@ def map_parity(cube, freq_params, xs, ys, zs, area, tb_gpu, vi_gpu, session=None
     kv = np.tile([[0.0, 0.0, -1.0]], (len(xs), 1))
     out = dict(n_pixels=int(len(xs)), n_freq=len(freq_params), max_dr_rsun=0.0, max_rel_dTb=0.0, max_dVI=0.0,
                n_pixel_freqs_over_tol=0, n_diving_pixel_freqs=0, n_diving_over_tol=0, max_rel_dTb_diving=0.0,
-               max_dr_rsun_diving=0.0, per_freq=[])
+               max_dr_rsun_diving=0.0, per_freq=[], oracle_seconds=0.0, oracle_nominal_ray_steps=0)
+    import time
     for f, p in enumerate(freq_params):
+        t0 = time.perf_counter()
         tb_ref, vi_ref, r_ref, _ = oracle.chain_bvec(cube, p["freq_hz"], p["dt"], p["n_steps"], p["record_stride"], xs,
-                                                     ys, zs, area, em_flag, s_max, return_paths=True)
+                                                     ys, zs, area, em_flag, s_max, return_paths=True,
+                                                     cache_gradient=True)
+        out["oracle_seconds"] += time.perf_counter() - t0
+        out["oracle_nominal_ray_steps"] += len(xs) * int(p["n_steps"])
         inside = np.all((r_ref >= lo) & (r_ref <= hi), axis=2)
         rad = np.where(inside, np.linalg.norm(r_ref, axis=2), np.inf)
         diving = rad.min(axis=0) < 1.0 + cell

@@ -46,6 +46,7 @@ struct MapArgs {
     int em_flag, s_max, use_bvec, order, cs_every_step;
     int s_mode;                          // RTGRFF_S_PER_STEP / RTGRFF_S_CUMULATIVE: which S a record carries
     int s_input;                         // the record's S scales the voxel's source term (--s-input-on)
+    int grff64;                          // 1: every voxel through the FP64 evaluation (RTGRFF_GRFF64=1, A/B and validation)
     double *tb, *vi;                     // [freq][ray]
     unsigned long long *active_steps;    // [0] active central steps, [1] steps with the pencil traced, [2] valid samples
 };
@@ -93,36 +94,38 @@ struct OutwardTransfer {
 
 // NEED_BETWEEN: gyroresonance on or theta from the B vector -> the previous voxel must be kept for
 // the between-voxel events; with the reference's packing (theta = 90, GR off) it is dead weight.
+// A voxel arrives as the float32 values the sampler produced (VoxLite + sin theta); its slab operator is
+// evaluated in float32 where that is well conditioned (voxel_op_mixed), the intensities live in FP64.
 template <bool NEED_BETWEEN>
 struct RecordTransfer {
     PolState<1> st;
     VoxLite prev;
     bool have_prev;
     __device__ __forceinline__ void init() { st.clear(); have_prev = false; }
-    __device__ __forceinline__ void push(const FreqC &f, const Voxel &v, const VoxLite &l, int flag, int smax)
+    __device__ __forceinline__ void push(const FreqC &f, const VoxLite &l, float sth, int flag, int smax, bool force64)
     {
-        if (!v.ok) { have_prev = false; return; }
+        if (!voxel_nonempty_f(l.dz, l.T, l.ne, l.B, l.cth)) { have_prev = false; return; }
         if (NEED_BETWEEN) {
-            if (have_prev && prev.B > 0.0f && l.B > 0.0f && between_needed_f(f, prev.cth, prev.B, l.cth, l.B, smax, v.gr_on))
-                st.apply(between_voxels(f, voxel_of(prev, flag, smax), v));
+            if (have_prev && prev.B > 0.0f && l.B > 0.0f && between_needed_f(f, prev.cth, prev.B, l.cth, l.B, smax, !(flag & 1)))
+                st.apply(between_voxels(f, voxel_of(prev, flag, smax), voxel_of(l, flag, smax)));
             prev = l;
             have_prev = true;
         }
-        st.apply(voxel_op<true>(f, v));
+        st.apply(voxel_op_mixed(f, l.dz, l.T, l.ne, l.B, l.cth, sth, l.scale, flag, smax, force64));
     }
     __device__ __forceinline__ void result(double &L, double &R) const { L = st.L[0]; R = st.R[0]; }
 };
 
 template <bool NEED_BETWEEN>
 struct OutwardTransferT : OutwardTransfer {
-    __device__ __forceinline__ void push(const FreqC &f, const Voxel &v, const VoxLite &l, int flag, int smax)
+    __device__ __forceinline__ void push(const FreqC &f, const VoxLite &l, float sth, int flag, int smax, bool force64)
     {
-        if (!v.ok) { have_prev = false; return; }
+        if (!voxel_nonempty_f(l.dz, l.T, l.ne, l.B, l.cth)) { have_prev = false; return; }
         if (NEED_BETWEEN) {
-            if (have_prev && prev.B > 0.0f && l.B > 0.0f && between_needed_f(f, l.cth, l.B, prev.cth, prev.B, smax, v.gr_on)) {
+            if (have_prev && prev.B > 0.0f && l.B > 0.0f && between_needed_f(f, l.cth, l.B, prev.cth, prev.B, smax, !(flag & 1))) {
                 // radiation crosses v -> prev: between_voxels(v, prev) lists the events in that order,
                 // folding outwards meets them last-first
-                const Between b = between_voxels(f, v, voxel_of(prev, flag, smax));
+                const Between b = between_voxels(f, voxel_of(l, flag, smax), voxel_of(prev, flag, smax));
                 fold(b.after);
                 if (b.qt) fold_qt(b.Q);
                 fold(b.before);
@@ -130,7 +133,7 @@ struct OutwardTransferT : OutwardTransfer {
             prev = l;
             have_prev = true;
         }
-        fold(voxel_op<true>(f, v));
+        fold(voxel_op_mixed(f, l.dz, l.T, l.ne, l.B, l.cth, sth, l.scale, flag, smax, force64));
     }
     __device__ __forceinline__ void result(double &L, double &R) const { L = accL; R = accR; }
 };
@@ -217,10 +220,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_MINB) render_map_kernel(const Map
                     if (isfinite(f.ne) && isfinite(f.te) && isfinite(f.b)) {
                         // Parms[14] = S * area (script/resample_with_ray_tracing.py:501): source factor S
                         const VoxLite lite = {ds, f.te, f.ne, f.b, cthf, a.s_input ? sv : 1.0f};
-                        Voxel vx = make_voxel_f(ds, f.te, f.ne, f.b, BVEC ? (double)cthf : 6.123233995736766e-17,
-                                                (double)sthf, a.em_flag, a.s_max);
-                        vx.scale = (double)lite.scale;
-                        tr.push(fq, vx, lite, a.em_flag, a.s_max);
+                        tr.push(fq, lite, sthf, a.em_flag, a.s_max, a.grff64 != 0);
                     }
                     px = x; py = y; pz = z;
                     first = false;

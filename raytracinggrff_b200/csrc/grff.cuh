@@ -15,6 +15,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "grff_fast.cuh"
 
 namespace rtgrff {
 
@@ -162,6 +163,7 @@ struct FreqC {
     double sn;    // kBres * nu: resonant field of harmonic s is sn / s
     double kff;   // kKff * kZeta / nu^2: free-free opacity prefactor
     float snf;    // sn rounded up to float32 (conservative side of between_needed_f)
+    FreqCF ff;    // float32 constants of the fast voxel evaluation (grff_fast.cuh)
 };
 
 __host__ __device__ __forceinline__ FreqC make_freq(double nu)
@@ -171,6 +173,14 @@ __host__ __device__ __forceinline__ FreqC make_freq(double nu)
     f.sn = kBres * nu;
     f.kff = kKff * kZeta * f.inv_nu2;
     f.snf = (float)(f.sn * (1.0 - 1e-6));
+    const double cv = kNup2 * f.inv_nu2;
+    f.ff.c_su = (float)(kNuB / nu);
+    f.ff.cv_hi = (float)cv;
+    f.ff.cv_lo = (float)(cv - (double)f.ff.cv_hi);
+    f.ff.lnl_cold = (float)(18.2 - f.ln_nu);
+    f.ff.lnl_hot = (float)(24.573 - f.ln_nu);
+    f.ff.kff = (float)f.kff;
+    f.ff.srcc = (float)(f.nu2 * kKbC2);
     return f;
 }
 
@@ -252,6 +262,39 @@ __device__ __forceinline__ DiagOp voxel_op(const FreqC &f, const Voxel &v)
     }
     // X is R where cos(theta) >= 0
     return (v.cth >= 0.0) ? DiagOp{aO, aX, bO, bX} : DiagOp{aX, aO, bX, bO};
+}
+
+// The per-ray kernels' voxel evaluation: float32 where it is well conditioned (grff_fast.cuh), the FP64
+// voxel_op otherwise (near the mode cut-offs and the gyro-resonance, anything non-finite).  Inputs are the
+// float32 sampler outputs; the emptiness tests are those of make_voxel_f.
+__device__ __forceinline__ bool voxel_nonempty_f(float dz, float T, float ne, float B, float cth)
+{
+    return (dz > 0.0f) & (dz < INFINITY) & (T > 0.0f) & (T < INFINITY) & (ne > 0.0f) & (ne < INFINITY) & (B >= 0.0f) &
+           (B < INFINITY) & (fabsf(cth) <= 1.0f);
+}
+
+// the FP64 fallback, out of line: it runs for the few voxels near a cut-off, and inlined it would put its
+// ~60 live FP64 values into the register budget of the callers' hot loops
+// (the four per-frequency numbers it needs travel by value: a reference into the kernel parameters would
+// make the compiler copy the whole parameter block to local memory)
+__device__ __noinline__ DiagOp voxel_op_slow(double nu2, double inv_nu2, double ln_nu, double kff, float dz, float T, float ne,
+                                             float B, float cth, float sth, float scale, int flag, int smax)
+{
+    FreqC f;
+    f.nu2 = nu2; f.inv_nu2 = inv_nu2; f.ln_nu = ln_nu; f.kff = kff;
+    Voxel v = make_voxel_f(dz, T, ne, B, (double)cth, (double)sth, flag, smax);
+    v.scale = (double)scale;
+    return voxel_op<true>(f, v);
+}
+
+__device__ __forceinline__ DiagOp voxel_op_mixed(const FreqC &f, float dz, float T, float ne, float B, float cth, float sth,
+                                                 float scale, int flag, int smax, bool force64)
+{
+    if (!force64) {
+        const FastOp o = voxel_op_f32(f.ff, dz, T, ne, B, cth, sth, scale, !(flag & 2));
+        if (o.ok) return DiagOp{(double)o.aL, (double)o.aR, (double)o.bL, (double)o.bR};
+    }
+    return voxel_op_slow(f.nu2, f.inv_nu2, f.ln_nu, f.kff, dz, T, ne, B, cth, sth, scale, flag, smax);
 }
 
 // One gyroresonance layer nu = s nu_B at interpolated plasma parameters.  Rare and heavy (lgamma,
@@ -505,11 +548,13 @@ struct OnlineTransfer {
     Voxel prev;
     bool have_prev;
     __device__ __forceinline__ void init() { st.clear(); have_prev = false; prev.ok = false; }
-    __device__ __forceinline__ void push(const FreqC &f, const Voxel &v)
+    // v holds float32 sampler values widened to double: the slab operator goes through voxel_op_mixed
+    __device__ __forceinline__ void push(const FreqC &f, const Voxel &v, bool force64)
     {
         if (!v.ok) { have_prev = false; return; }
         if (have_prev && prev.B > 0.0 && v.B > 0.0) st.apply(between_voxels(f, prev, v));
-        st.apply(voxel_op<true>(f, v));
+        st.apply(voxel_op_mixed(f, (float)v.dz, (float)v.T, (float)v.ne, (float)v.B, (float)v.cth, (float)v.sth, (float)v.scale,
+                                (v.gr_on ? 0 : 1) | (v.ff_on ? 0 : 2), v.smax, force64));
         prev = v;
         have_prev = true;
     }
@@ -536,6 +581,7 @@ struct EmissionArgs {
     int64_t n_rec, n_rays;
     double area, freq0, log_step;
     int n_freq, em_flag, s_max;
+    int grff64;                      // 1: FP64 voxel evaluation throughout (RTGRFF_GRFF64=1)
     double *tb, *vi;                 // (ray, freq)
 };
 
@@ -558,7 +604,7 @@ __global__ void __launch_bounds__(128) emission_rays_kernel(const EmissionArgs a
         Voxel v = make_voxel((double)a.ds[o], (double)te, (double)ne, (double)b, 90.0, a.em_flag, a.s_max);
         // Parms[14] = S * area (script/resample_with_ray_tracing.py:501) -> source factor S where S > 0
         if (a.s_input && a.s[o] > 0.0f) v.scale = (double)a.s[o];
-        tr.push(fq, v);
+        tr.push(fq, v, a.grff64 != 0);
     }
     double tb, vi;
     tb_vi(tr.st.L[0], tr.st.R[0], nu, a.area, tb, vi);

@@ -128,7 +128,7 @@ static int d2h(rtgrff_ctx *c, void *dst, const void *src, size_t bytes)
 // inside 93 ms of copies).  Large calls therefore go through pinned bounce buffers in chunks: the
 // host packs chunk k+1 and unpacks chunk k-1 with a few threads while the DMA engines move chunk k
 // in both directions (H2D on the compute stream, D2H on the copy stream) and the kernel runs on it.
-static int pipeline_enabled()
+static int pipeline_default()
 {
     static int v = -1;
     if (v < 0) {
@@ -206,7 +206,7 @@ static bool is_pinned_host(const void *p)
 static int d2h_large(rtgrff_ctx *c, void *dst, const void *src, size_t bytes)
 {
     if (!bytes) return RTGRFF_OK;
-    if (is_pinned_host(dst) || bytes < ((size_t)8 << 20) || !pipeline_enabled()) {
+    if (is_pinned_host(dst) || bytes < ((size_t)8 << 20) || !c->pipeline) {
         RT_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
         RT_CUDA(cudaStreamSynchronize(c->stream));
         return RTGRFF_OK;
@@ -234,7 +234,7 @@ static int d2h_large(rtgrff_ctx *c, void *dst, const void *src, size_t bytes)
 static int h2d_large(rtgrff_ctx *c, void *dst, const void *src, size_t bytes)
 {
     if (!bytes) return RTGRFF_OK;
-    if (is_pinned_host(src) || bytes < ((size_t)8 << 20) || !pipeline_enabled()) {
+    if (is_pinned_host(src) || bytes < ((size_t)8 << 20) || !c->pipeline) {
         RT_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
         return RTGRFF_OK;
     }
@@ -300,6 +300,18 @@ static int cs_every_step()
     return v;
 }
 
+static int grff64()
+{
+    // RTGRFF_GRFF64=1: the per-ray kernels evaluate every voxel in FP64 (A/B switch; default: float32 where
+    // well conditioned, see grff_fast.cuh)
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("RTGRFF_GRFF64");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v;
+}
+
 static int trace_variant()
 {
     // RTGRFF_MODE selects the ray stepper: 0 (default) FP64 master state + FP32 cell-relative RHS with a
@@ -341,6 +353,7 @@ static int ctx_create(int device, void *stream, bool caller_stream, rtgrff_ctx *
     rtgrff_ctx *c = new (std::nothrow) rtgrff_ctx();
     if (!c) return fail(RTGRFF_ENOMEM, "out of host memory");
     c->device = device;
+    c->pipeline = pipeline_default();
     cudaError_t e = cudaSuccess;
     cudaDeviceProp prop;
     if ((e = cudaGetDeviceProperties(&prop, device)) == cudaSuccess) {
@@ -415,6 +428,13 @@ int rtgrff_ctx_synchronize(rtgrff_ctx *c)
 {
     RT_USE(c);
     RT_CUDA(cudaStreamSynchronize(c->stream));
+    return RTGRFF_OK;
+}
+
+int rtgrff_ctx_set_pipeline(rtgrff_ctx *c, int enabled)
+{
+    if (!c) return fail(RTGRFF_EINVAL, "null context");
+    c->pipeline = enabled ? 1 : 0;
     return RTGRFF_OK;
 }
 
@@ -836,7 +856,7 @@ int rtgrff_sample(rtgrff_ctx *c, int64_t n_rec, int64_t n_rays, const float *pos
     RT_TRY(c->in1.reserve(n * sizeof(float)));
     RT_TRY(h2d(c, c->in2, ray_start, (size_t)n_rays * 3 * sizeof(float)));
     a.pos_aos = c->in0.as<float>(); a.s32 = c->in1.as<float>(); a.ray_start = c->in2.as<float>();
-    if (pipeline_enabled() && n * 33 >= kPipeMinBytes) {
+    if (c->pipeline && n * 33 >= kPipeMinBytes) {
         RT_TRY(prepare_sampler(c, a, r_sun_cm, fill_ne, fill_te, fill_b));
         return sample_pipelined(c, a, pos, s, ne, te, b, ds, valid);
     }
@@ -899,7 +919,7 @@ static int run_slice(rtgrff_ctx *c, int npix, int nz, int nf, const double *rpar
     RT_TRY(c->out1.reserve((size_t)npix * sizeof(int32_t)));
     RT_CUDA(cudaMemsetAsync(c->out1.p, 0xff, (size_t)npix * sizeof(int32_t), c->stream));
     double *d_parms = c->in0.as<double>();
-    if (pipeline_enabled() && pb >= kPipeMinBytes && pix_b > 0) {
+    if (c->pipeline && pb >= kPipeMinBytes && pix_b > 0) {
         int64_t pix_per_chunk = (int64_t)(kPipeChunkBytes / pix_b);
         if (pix_per_chunk < 1) pix_per_chunk = 1;
         const int64_t n_chunk = (npix + pix_per_chunk - 1) / pix_per_chunk;
@@ -1051,6 +1071,7 @@ int rtgrff_emission_traced(rtgrff_ctx *c, double pixel_area_cm2, double freq0_hz
     a.n_rec = c->smp_n; a.n_rays = c->smp_rays;
     a.area = pixel_area_cm2; a.freq0 = freq0_hz; a.log_step = freq_log_step;
     a.n_freq = n_freq; a.em_flag = em_flag; a.s_max = s_max;
+    a.grff64 = grff64();
     a.tb = c->out0.as<double>(); a.vi = c->out1.as<double>();
     RT_CUDA(cudaEventRecord(c->ev0, c->stream));
     emission_rays_kernel<<<blocks_for((int64_t)n, 128), 128, 0, c->stream>>>(a);
@@ -1138,6 +1159,7 @@ int rtgrff_render_map(rtgrff_ctx *c, int64_t n_rays, const double *x_start, cons
     a.em_flag = em_flag; a.s_max = s_max; a.use_bvec = use_bvec; a.order = voxel_order;
     a.cs_every_step = cs_every_step();
     a.s_mode = s_mode; a.s_input = s_input_on ? 1 : 0;
+    a.grff64 = grff64();
     a.tb = dtb; a.vi = dvi;
     a.active_steps = c->counters.as<unsigned long long>();
     const dim3 block(RT_BLOCK);

@@ -32,12 +32,13 @@ def omega_pe_from_ne(ne):
     return np.nan_to_num(w, nan=0.0, posinf=0.0, neginf=0.0)
 
 
-def corona_cube(grid_n, extent, active_region=False, b0=2.0, dtype=np.float64):
+def corona_cube(grid_n, extent, active_region=False, b0=2.0, dtype=np.float64, x_slice=None):
     """Analytic corona on ``linspace(-extent, extent, grid_n)^3`` (x slowest, z fastest; the
     observer sits on +z and solar north is +y).  Returns a dict with the 1-D grids and the cubes
-    ``ne, te, b, bx, by, bz, omega_pe``."""
+    ``ne, te, b, bx, by, bz, omega_pe``.  ``x_slice``: only those x planes of the cubes (a 512^3 cube in
+    slabs keeps the temporaries small); the grids stay the full ones."""
     g = np.linspace(-extent, extent, grid_n)
-    x = g[:, None, None]
+    x = (g if x_slice is None else g[x_slice])[:, None, None]
     y = g[None, :, None]
     z = g[None, None, :]
     r2 = x * x + y * y + z * z
