@@ -20,6 +20,6 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --cs
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:render_map -s 3 -c 1 -o $O/r2a_render_map \
     python bench.py --steps 1 --warmup 3 --no-extras --no-cpu-baseline > $O/r2a_ncu_full.log 2>&1
 timeout 300 python scripts/stage_bench.py --quick > $O/r2a_stage.json 2> $O/r2a_stage.err && \
-timeout 900 ncu --set full --clock-control none --import-source on -k "regex:sample_paths|grff_slice|emission_rays" -c 6 -o $O/r2a_stage_kernels \
+timeout 900 ncu --set full --clock-control none --import-source on -k "regex:sample_paths|grff_slice|emission_rays" -c 40 -o $O/r2a_stage_kernels \
     python scripts/stage_bench.py --quick > $O/r2a_ncu_stage.log 2>&1
 ls -la $O | tail -30
