@@ -256,3 +256,19 @@ def test_gather_image_single_rank_and_shard_layout(session):
             for r in range(world):
                 rows, mr = rdist.c_shard_rows(n, world, r)
                 assert np.array_equal(rows, rdist.rows_of_rank(n, world, r)) and mr == rdist.max_rows_per_rank(n, world)
+
+
+@pytest.mark.parametrize("backend", ["fused", "device", "fastgrff"])
+def test_workers_split_rays_over_gpus_without_changing_the_map(backend):
+    """``--workers N`` (script/resample_with_ray_tracing.py:333-352: contiguous ray chunks, concatenated): here the
+    chunks go to the visible GPUs, each with its own context and cube replica.  Rays are independent, so the map
+    is the single-worker map bit for bit — also when the chunks do not divide the image evenly."""
+    from raytracinggrff_b200.workflow import run_ray_tracing_emission
+    c = synthetic.corona_cube(48, 3.0)
+    kw = dict(N_pix=10, X_fov=1.3, freq_hz=90e6, z_observer=3.0, dt=6e-3, n_steps=1500, record_stride=8,
+              grff_backend=backend, verbose=False)
+    one = run_ray_tracing_emission(c, n_workers=1, **kw)
+    many = run_ray_tracing_emission(c, n_workers=3, **kw)
+    assert (one["emission_cube"] > 0).mean() > 0.3
+    assert np.array_equal(one["emission_cube"], many["emission_cube"])
+    assert np.array_equal(one["emission_polVI_cube"], many["emission_polVI_cube"])
