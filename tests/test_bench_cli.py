@@ -43,3 +43,19 @@ def test_cuda_arm_fails_loudly_without_a_gpu():
     p = _run(["--config", "c3", "--steps", "1", "--warmup", "3"])
     assert p.returncode != 0
     assert "CUDA" in (p.stderr + p.stdout)
+
+
+def test_reference_numpy_leg_runs_the_unmodified_reference():
+    """bench.py's `extras.reference_numpy`: the UNMODIFIED reference package (baseline/_ref, installed by
+    baseline/install_ref.sh) timed in a child process: ray_trace single-process and over a process pool, the CPU sampler."""
+    import pytest
+    sys.path.insert(0, str(ROOT))
+    import bench
+    if not (ROOT / "baseline" / "_ref" / "raytracingGRFF").is_dir():
+        pytest.skip("baseline/_ref is not installed here")
+    w = bench.workload("c3", 1)
+    w["grid_n"] = 32
+    d = bench.reference_numpy_timing(None, w, budget_rays=64, n_steps=12)
+    assert "unavailable" not in d, d
+    assert d["rays"] == 64 and d["ray_trace_single_process_ray_steps_per_s"] > 0
+    assert d["ray_trace_process_pool_ray_steps_per_s"] > 0 and d["sampler_samples_per_s"] > 0
