@@ -88,6 +88,9 @@ struct rtgrff_ctx {
     int pipeline = 1;                // chunked pinned host pipelines on (RTGRFF_PIPELINE, rtgrff_ctx_set_pipeline)
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t chunk_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // in[2], kernel[2], out[2]
+    // fork / join of the per-frequency launches of the fused map (RT_FREQ_PER_LAUNCH = 1)
+    cudaStream_t fstream[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t fev[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     void *pinned[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t pinned_cap[4] = {0, 0, 0, 0};
     int64_t launches = 0;

@@ -30,7 +30,13 @@ struct FreqDev {
     FreqC fq;
 };
 
-constexpr int kMaxFreqPerLaunch = 16;
+// RT_FREQ_PER_LAUNCH = 1: one launch per frequency (on a few streams, so that the launches still overlap): the
+// per-frequency constants then sit at fixed offsets of the constant bank and become instruction operands, where
+// the multi-frequency launch indexes them with blockIdx.y (an LDC with a register index in the inner loops).
+#ifndef RT_FREQ_PER_LAUNCH
+#define RT_FREQ_PER_LAUNCH 16
+#endif
+constexpr int kMaxFreqPerLaunch = RT_FREQ_PER_LAUNCH;
 
 struct MapArgs {
     RayCube cube;
@@ -143,7 +149,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_MINB) render_map_kernel(const Map
 {
     constexpr bool NEED_BETWEEN = BVEC || GR;
     const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int fi = blockIdx.y;
+    const int fi = (kMaxFreqPerLaunch == 1) ? 0 : (int)blockIdx.y;
     const bool has_ray = slot < a.n_rays;
     const int64_t ray = (has_ray && a.ray_order) ? (int64_t)a.ray_order[slot] : slot;
     const RayCube &C = a.cube;

@@ -416,6 +416,10 @@ int rtgrff_ctx_destroy(rtgrff_ctx *c)
     if (c->ev1) cudaEventDestroy(c->ev1);
     for (cudaEvent_t &e : c->chunk_ev)
         if (e) cudaEventDestroy(e);
+    for (cudaEvent_t &e : c->fev)
+        if (e) cudaEventDestroy(e);
+    for (cudaStream_t &q : c->fstream)
+        if (q) cudaStreamDestroy(q);
     for (void *&h : c->pinned)
         if (h) cudaFreeHost(h);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -1185,10 +1189,25 @@ int rtgrff_render_map(rtgrff_ctx *c, int64_t n_rays, const double *x_start, cons
         return cost(x) > cost(y);
     });
     // the per-frequency constants travel in the kernel parameters: kMaxFreqPerLaunch frequencies per launch
+    const bool fork = kMaxFreqPerLaunch == 1 && n_freq > 1;
+    cudaStream_t main_stream = c->stream;
+    if (fork) {
+        for (int q = 0; q < 8; ++q)
+            if (!c->fstream[q]) RT_CUDA(cudaStreamCreateWithFlags(&c->fstream[q], cudaStreamNonBlocking));
+        for (int q = 0; q < 9; ++q)
+            if (!c->fev[q]) RT_CUDA(cudaEventCreateWithFlags(&c->fev[q], cudaEventDisableTiming));
+        RT_CUDA(cudaEventRecord(c->fev[8], main_stream));
+        for (int q = 0; q < 8; ++q) RT_CUDA(cudaStreamWaitEvent(c->fstream[q], c->fev[8], 0));
+    }
     for (int f0 = 0; f0 < n_freq; f0 += kMaxFreqPerLaunch) {
     a.n_freq = n_freq - f0 < kMaxFreqPerLaunch ? n_freq - f0 : kMaxFreqPerLaunch;
     for (int f = 0; f < a.n_freq; ++f) a.freqs[f] = fd[f0 + f];
     const dim3 grid(blocks_for(n_rays, RT_BLOCK), (unsigned int)a.n_freq);
+    struct StreamSwap {           // the launches below go to c->stream
+        rtgrff_ctx *c; cudaStream_t keep;
+        ~StreamSwap() { c->stream = keep; }
+    } swap{c, main_stream};
+    if (fork) c->stream = c->fstream[f0 % 8];
     switch (variant) {
         RT_MAP_CASE(0, false, 0, false, false) RT_MAP_CASE(1, false, 0, false, true)
         RT_MAP_CASE(2, false, 0, true, false) RT_MAP_CASE(3, false, 0, true, true)
@@ -1200,6 +1219,12 @@ int rtgrff_render_map(rtgrff_ctx *c, int64_t n_rays, const double *x_start, cons
         RT_MAP_CASE(14, true, 1, true, false) RT_MAP_CASE(15, true, 1, true, true)
     }
     RT_TRY(launched(c, "render_map_kernel"));
+    }
+    if (fork) {
+        for (int q = 0; q < 8; ++q) {
+            RT_CUDA(cudaEventRecord(c->fev[q], c->fstream[q]));
+            RT_CUDA(cudaStreamWaitEvent(main_stream, c->fev[q], 0));
+        }
     }
 #undef RT_MAP_CASE
     RT_CUDA(cudaEventRecord(c->ev1, c->stream));

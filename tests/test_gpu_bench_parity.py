@@ -10,7 +10,8 @@ at full image size, against the oracle chain (ray_trace -> sampler -> Parms with
   all 16 frequencies 20 - 300 MHz with the low-band presets, every 64th pixel.
 
 Tolerances: paths <= 1e-5 R_sun, T_b <= 1e-4 relative, V/I <= 1e-4 absolute.  Pixels whose ray grazes the
-r = 1 density discontinuity are chaotic (oracle/parity.py); their fraction is bounded and only they may breach.
+r = 1 density discontinuity are chaotic (oracle/parity.py): only rays that reach it may breach, and the share
+that does is bounded (measured on config 4: 40 of 8192 pixel-frequencies, 0.5 %).
 """
 import sys
 from pathlib import Path
@@ -36,11 +37,13 @@ def _render_full(session, w, fps, area):
     return xs, ys, zs, tb, vi, st
 
 
-def _assert_parity(par, max_diving_frac):
+def _assert_parity(par, max_chaotic_frac):
+    """Every pixel whose ray stays clear of the r = 1 density discontinuity is within the tolerances; of the rays
+    that reach it (at GHz frequencies: the whole disc) only the grazing ones are chaotic — a small, bounded share."""
     msg = {k: v for k, v in par.items() if k != "per_freq"}
     assert par["n_pixel_freqs_over_tol"] == 0, (msg, par["per_freq"])
     assert par["max_dr_rsun"] <= 1e-5 and par["max_rel_dTb"] <= 1e-4 and par["max_dVI"] <= 1e-4, msg
-    assert par["frac_diving"] <= max_diving_frac, msg
+    assert par["n_diving_over_tol"] <= max_chaotic_frac * par["n_pixels"] * par["n_freq"], msg
     print("parity:", msg)
     for row in par["per_freq"]:
         print("  ", row)
@@ -63,7 +66,7 @@ def test_config4_bench_variant_matches_oracle_chain(oracle, session):
     assert par["n_pixels"] == 1024 and par["n_freq"] == 8
     # gyroresonance must matter somewhere on this cube (active region, GHz frequencies)
     assert max(r["max_abs_vi"] for r in par["per_freq"]) > 1e-3
-    _assert_parity(par, max_diving_frac=0.08)
+    _assert_parity(par, max_chaotic_frac=0.01)
 
 
 def test_config5_bench_variant_matches_oracle_chain(oracle, session):
@@ -86,6 +89,6 @@ def test_config5_bench_variant_matches_oracle_chain(oracle, session):
                                     pixel_area_cm2=area, r_sun_cm=6.957e10, em_flag=4, s_max=30, use_bvec=True)
     par = parity.map_parity(c, fps, xs[sel], ys[sel], zs[sel], area, tb, vi, session=session)
     assert par["n_pixels"] == 1024 and par["n_freq"] == 16
-    _assert_parity(par, max_diving_frac=0.08)
+    _assert_parity(par, max_chaotic_frac=0.01)
     # steps longer than a cell at the lowest frequencies (1.1 cells + pencil): still the FP32 stepper
     assert fps[0]["dt"] * (2.998e10 / 6.96e10) * 3 / (g[1] - g[0]) > 1.0
