@@ -173,7 +173,8 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_MINB) render_map_kernel(const Map
         }
     }
     bool alive = has_ray;
-    double s_step = CS ? 0.0 : 1.0, s_cum = 1.0;
+    float s_step = CS ? 0.0f : 1.0f;
+    double s_cum = 1.0;
     const bool cumulative = CS && a.s_mode == RTGRFF_S_CUMULATIVE;
     unsigned int n_samples = 0;
     const int n_steps = (int)fp.n_steps, stride = (int)fp.stride;     // < 2^31, checked on the host
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_MINB) render_map_kernel(const Map
             next_rec += stride;
             if (!tail_done) {
                 // --- sampler (float32, gpu_raytrace.py:642-650) ---
-                const float x = (float)s.rx, y = (float)s.ry, z = (float)s.rz, sv = (float)(cumulative ? s_cum : s_step);
+                const float x = (float)s.rx, y = (float)s.ry, z = (float)s.rz, sv = cumulative ? (float)s_cum : s_step;
                 if (sample_valid(x, y, z, sv)) {
                     ++n_samples;
                     float3 bv = make_float3(0.f, 0.f, 0.f);

@@ -160,10 +160,12 @@ __device__ __forceinline__ Deriv32 rhs32(const RayCube &C, Cell &cache, bool edg
                                          float dx, float dy, float dz, float kx, float ky, float kz)
 {
     Deriv32 d;
-    d.vx = d.vy = d.vz = d.gx = d.gy = d.gz = 0.0f;
     float tx = px + dx, ty = py + dy, tz = pz + dz;
     if (!(in_unit(tx) & in_unit(ty) & in_unit(tz))) {
-        if (!move_cell(C, cache, edge, px, py, pz, tx, ty, tz)) return d;
+        if (!move_cell(C, cache, edge, px, py, pz, tx, ty, tz)) {
+            d.vx = d.vy = d.vz = d.gx = d.gy = d.gz = 0.0f;
+            return d;
+        }
     }
     const float2 tz2 = make_float2(tz, tz), ty2 = make_float2(ty, ty), tx2 = make_float2(tx, tx);
     // {omega_pe, d/dx}
@@ -176,15 +178,16 @@ __device__ __forceinline__ Deriv32 rhs32(const RayCube &C, Cell &cache, bool edg
         __ffma2_rn(__ffma2_rn(cache.hyz, tz2, cache.hy), ty2, __ffma2_rn(cache.hz, tz2, cache.h0)));
     const float w = wg.x;
     const float om2 = fmaf(w, w, fmaf(kx, kx, fmaf(ky, ky, kz * kz)));
-    // valid = isfinite(omega_pe) & isfinite(omega) & (omega > 0)   (build_rays.py:169); a non-finite
-    // omega_pe or k makes omega^2 non-finite, so one range test on omega^2 covers all three:
-    // 0 < omega^2 < inf  <=>  bit pattern in [1, 0x7f7fffff]
-    if (__float_as_uint(om2) - 1u >= 0x7f7fffffu) return d;
     float inv_om;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv_om) : "f"(om2));   // MUFU.RSQ, 2 ulp; omega^2 ~ 1e17
     const float a = w * inv_om;
     d.vx = kx * inv_om; d.vy = ky * inv_om; d.vz = kz * inv_om;
     d.gx = a * wg.y; d.gy = a * gg.x; d.gz = a * gg.y;
+    // valid = isfinite(omega_pe) & isfinite(omega) & (omega > 0)   (build_rays.py:169); a non-finite
+    // omega_pe or k makes omega^2 non-finite, so one range test on omega^2 covers all three:
+    // 0 < omega^2 < inf  <=>  bit pattern in [1, 0x7f7fffff].  The invalid stage (a zero derivative) is the
+    // rare case: the zeros are written on that branch only, not materialised ahead of every evaluation.
+    if (__builtin_expect(__float_as_uint(om2) - 1u >= 0x7f7fffffu, 0)) d.vx = d.vy = d.vz = d.gx = d.gy = d.gz = 0.0f;
     return d;
 }
 
@@ -233,7 +236,7 @@ __host__ __device__ __forceinline__ StepConst make_step_const(const RayCube &C, 
 // update is then exactly zero too, for ever).
 template <bool CS>
 __device__ __forceinline__ bool step32(const RayCube &C, const StepConst &K, Cell &cache, State &s, bool want_s,
-                                       double &s_step)
+                                       float &s_step)
 {
     const double fx = (s.rx - C.x0) * C.idx, fy = (s.ry - C.y0) * C.idy, fz = (s.rz - C.z0) * C.idz;
     if (cache.off < 0) {
@@ -269,9 +272,13 @@ __device__ __forceinline__ bool step32(const RayCube &C, const StepConst &K, Cel
 #pragma unroll          // the four stages unrolled (constant weights), the three rays of a step rolled
         for (int st = 0; st < 4; ++st) {
             const Deriv32 d = rhs32(C, cache, edge, px, py, pz, dx, dy, dz, skx, sky, skz);
-            const float w = (st == 0 || st == 3) ? 1.0f : 2.0f;
-            avx = fmaf(w, d.vx, avx); avy = fmaf(w, d.vy, avy); avz = fmaf(w, d.vz, avz);
-            agx = fmaf(w, d.gx, agx); agy = fmaf(w, d.gy, agy); agz = fmaf(w, d.gz, agz);
+            if (st == 0) {        // (0 + x is not x for x = -0: spelled out, the compiler would keep six FADDs)
+                avx = d.vx; avy = d.vy; avz = d.vz; agx = d.gx; agy = d.gy; agz = d.gz;
+            } else {
+                const float w = (st == 3) ? 1.0f : 2.0f;
+                avx = fmaf(w, d.vx, avx); avy = fmaf(w, d.vy, avy); avz = fmaf(w, d.vz, avz);
+                agx = fmaf(w, d.gx, agx); agy = fmaf(w, d.gy, agy); agz = fmaf(w, d.gz, agz);
+            }
             const float a = (st < 2) ? 1.0f : 2.0f;   // stages 2, 3 at dt/2, stage 4 at dt (K.h* are half steps)
             dx = fmaf(a * K.hx, d.vx, qx); dy = fmaf(a * K.hy, d.vy, qy); dz = fmaf(a * K.hz, d.vz, qz);
             const float ak = -a * K.hk;
@@ -309,7 +316,7 @@ __device__ __forceinline__ bool step32(const RayCube &C, const StepConst &K, Cel
                 ox = eps * e2x; oy = eps * e2y; oz = eps * e2z;
             } else {
                 const float cx = d1y * ddz - d1z * ddy, cy = d1z * ddx - d1x * ddz, cz = d1x * ddy - d1y * ddx;
-                s_step = (double)__fdividef(fabsf(fmaf(cx, tx, fmaf(cy, ty, cz * tz))), eps * eps);
+                s_step = __fdividef(fabsf(fmaf(cx, tx, fmaf(cy, ty, cz * tz))), eps * eps);
             }
         }
     }

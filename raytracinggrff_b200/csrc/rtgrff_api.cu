@@ -146,9 +146,9 @@ static int host_threads()
         int n = e ? atoi(e) : 0;
         if (n <= 0) {
             n = (int)std::thread::hardware_concurrency();
-            n = n >= 16 ? 8 : (n >= 4 ? n / 2 : 1);
+            n = n >= 8 ? (3 * n) / 4 : (n >= 4 ? n / 2 : 1);   // leave cores to the caller's own threads
         }
-        v = n > 32 ? 32 : n;
+        v = n > 16 ? 16 : n;
     }
     return v;
 }

@@ -21,7 +21,7 @@ enum { MODE_FAST32 = 0, MODE_F64 = 1, MODE_F64_LERP64 = 2 };
 // RHS evaluations skipped on the other steps.  Cumulative mode needs every step.
 template <bool CS, int MODE>
 __device__ __forceinline__ bool advance_ray(const RayCube &C, const StepConst &K, Cell &cache, State &s, double dt,
-                                            double perturb_ratio, bool want_s, double &s_step)
+                                            double perturb_ratio, bool want_s, float &s_step)
 {
     bool moved;
     if (MODE == MODE_FAST32) {
@@ -30,10 +30,10 @@ __device__ __forceinline__ bool advance_ray(const RayCube &C, const StepConst &K
         constexpr bool L64 = (MODE == MODE_F64_LERP64);
         const State s0 = s;
         s = rk4_step<L64>(C, s0, dt);
-        if (CS && want_s) s_step = cross_section_ratio<L64>(C, s0, s, dt, perturb_ratio);
+        if (CS && want_s) s_step = (float)cross_section_ratio<L64>(C, s0, s, dt, perturb_ratio);
         moved = in_cube(C, s0.rx, s0.ry, s0.rz) && state_differs(s, s0);
     }
-    if (CS && !moved) s_step = nan("");
+    if (CS && !moved) s_step = nanf("");
     return moved;
 }
 
@@ -73,7 +73,8 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_MINB) trace_rays_kernel(const Tra
         }
     }
     bool alive = has_ray;
-    double s_step = 0.0, s_cum = 1.0;
+    float s_step = 0.0f;        // the ratio is a float32 quantity (MUFU-normalised pencil basis); the sampler casts it anyway
+    double s_cum = 1.0;
     unsigned long long moved_steps = 0;
     int64_t rec = 0, next_rec = 0;
     const size_t n = (size_t)a.n_rays;
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_MINB) trace_rays_kernel(const Tra
             if (has_ray) {
                 double *o = a.rec_pos + (size_t)rec * 3 * n + (size_t)ray;
                 o[0] = s.rx; o[n] = s.ry; o[2 * n] = s.rz;
-                if (CS) a.rec_s[(size_t)rec * n + (size_t)ray] = (a.s_mode == RTGRFF_S_CUMULATIVE) ? s_cum : s_step;
+                if (CS) a.rec_s[(size_t)rec * n + (size_t)ray] = (a.s_mode == RTGRFF_S_CUMULATIVE) ? s_cum : (double)s_step;
             }
             ++rec;
             next_rec += a.stride;
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_MINB) trace_rays_kernel(const Tra
     }
     // frozen tail: constant records
     if (has_ray) {
-        const double sv = (a.s_mode == RTGRFF_S_CUMULATIVE) ? s_cum : s_step;
+        const double sv = (a.s_mode == RTGRFF_S_CUMULATIVE) ? s_cum : (double)s_step;
         for (; rec < a.n_rec; ++rec) {
             double *o = a.rec_pos + (size_t)rec * 3 * n + (size_t)ray;
             o[0] = s.rx; o[n] = s.ry; o[2 * n] = s.rz;

@@ -89,6 +89,20 @@ def main():
                 print(f"{label} f={f/1e6:7.1f} MHz T={p['n_steps']:6d} stride={p['record_stride']}: {ms:7.1f} ms  "
                       f"active {st['active_ray_steps']/ms/1e6:.2f} G ray-steps/s  ({st['active_ray_steps']/st['nominal_ray_steps']:.2f} active)")
             print(f"{label} total {tot:.1f} ms")
+    if which == "c4all":
+        # the bench call itself: one render_map with all 8 frequencies, 4x8 tiles; device time of the whole call
+        c = synthetic.corona_cube(256, 3.0, active_region=True)
+        ses.set_omega_cube(c["omega_pe"], c["x_grid"], c["y_grid"], c["z_grid"])
+        ses.set_field_cubes(c["x_grid"], c["y_grid"], c["z_grid"], c["ne"], c["te"], c["b"], c["bx"], c["by"], c["bz"])
+        xs, ys, zs, kv = synthetic.ray_launch_geometry(512, 1.44, 3.0)
+        area = (2 * 1.44 / 512 * 6.957e10) ** 2
+        freqs = synthetic.log_frequencies(75e6, 8, np.log10(20.0) / 7)
+        fps = [dict(freq_hz=float(f), **synthetic.frequency_scaled_params(float(f))) for f in freqs]
+        ms = []
+        for _ in range(5):
+            tb, vi, st = ses.render_map(xs, ys, zs, fps, pixel_area_cm2=area, em_flag=4, use_bvec=True, image_shape=(512, 512))
+            ms.append(ses.ctx.last_kernel_ms)
+        print("c4all ms:", " ".join(f"{m:.1f}" for m in ms), " best", min(ms), " checksum", float(tb.sum()), float(np.abs(vi).sum()))
     if which == "ncu_c4f":
         # one fused launch of the bench configuration at one frequency (RTGRFF_FIDX) for ncu
         c = synthetic.corona_cube(256, 3.0, active_region=True)
