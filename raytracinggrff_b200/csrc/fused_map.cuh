@@ -34,7 +34,7 @@ struct FreqDev {
 // per-frequency constants then sit at fixed offsets of the constant bank and become instruction operands, where
 // the multi-frequency launch indexes them with blockIdx.y (an LDC with a register index in the inner loops).
 #ifndef RT_FREQ_PER_LAUNCH
-#define RT_FREQ_PER_LAUNCH 16
+#define RT_FREQ_PER_LAUNCH 1
 #endif
 constexpr int kMaxFreqPerLaunch = RT_FREQ_PER_LAUNCH;
 
