@@ -139,28 +139,6 @@ def straight_los_case(N_pix=256, N_z=400, X_fov=1.44, dz0=3e-4, r_min=0.9999999,
     return out
 
 
-def los_sampler_case(n_pix=256, n_steps=256, grid_n=128, seed=0):
-    """BASELINE config 1: the synthetic LOS-sampling case of the reference benchmark
-    (bench_raytrace.py:126-151): Gaussian n_e, linear T and B on [-2,2]^3, jittered straight rays
-    from z = 2.5, sample spacing 0.02, S = 1.  Same RNG call sequence, hence the same arrays."""
-    rng = np.random.default_rng(seed)
-    g = np.linspace(-2.0, 2.0, grid_n, dtype=np.float32)
-    x, y, z = np.meshgrid(g, g, g, indexing="ij")
-    ne = (1.0e8 + 2.0e8 * np.exp(-(x * x + y * y + z * z))).astype(np.float32)
-    te = (1.0e6 + 2.0e6 * (x + 2 * y - z)).astype(np.float32)
-    b = (2.0 + x - y + 0.5 * z).astype(np.float32)
-    n_rays = n_pix * n_pix
-    origin_xy = rng.uniform(-1.2, 1.2, size=(n_rays, 2)).astype(np.float32)
-    origin = np.column_stack([origin_xy, np.full(n_rays, 2.5, dtype=np.float32)])
-    dirs = np.tile(np.array([[0.0, 0.0, -1.0]], dtype=np.float32), (n_rays, 1))
-    dirs[:, 0:2] += rng.normal(scale=0.02, size=(n_rays, 2)).astype(np.float32)
-    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
-    s = (np.arange(n_steps, dtype=np.float32) * 0.02)[:, None]
-    r_record = origin[None, :, :] + s[:, :, None] * dirs[None, :, :]
-    s_arr = np.ones((n_steps, n_rays), dtype=np.float32)
-    return g, g.copy(), g.copy(), ne, te, b, r_record, s_arr, origin
-
-
 @functools.lru_cache(maxsize=16)
 def tile_order(n_x, n_y, tile_w=8, tile_h=4):
     """Permutation of the flat pixel indices p = i*n_x + j that walks the image in tile_w x tile_h

@@ -9,6 +9,8 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))     # cases.los_sampler_case: the reference benchmark's fixture
+import cases  # noqa: E402
 from raytracinggrff_b200 import RaySession, synthetic  # noqa: E402
 from oracle import oracle  # noqa: E402
 
@@ -141,7 +143,7 @@ def main():
             _, _, st = ses.render_map(xs, ys, zs, [(f, p["dt"], p["n_steps"], p["record_stride"])], kvec_in_norm=kv, pixel_area_cm2=area)
             print(st)
     if which in ("all", "c1"):
-        args = synthetic.los_sampler_case(256, 256, 128, seed=0)
+        args = cases.los_sampler_case(256, 256, 128, seed=0)
         ses.set_field_cubes(args[0], args[1], args[2], args[3], args[4], args[5])
         t = timeit(lambda: ses.sample(args[6], args[7], args[8], 6.957e10))
         print(f"C1 sampler e2e (H2D+kernel+D2H): {t*1e3:.1f} ms  {256*256*256/t:.3e} samples/s")

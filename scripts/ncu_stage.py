@@ -9,13 +9,15 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))     # cases.los_sampler_case: the reference benchmark's fixture
+import cases  # noqa: E402
 from raytracinggrff_b200 import RaySession, synthetic  # noqa: E402
 
 which = sys.argv[1]
 ses = RaySession()
 ses.ctx.set_pipeline(False)            # one launch over the whole input
 if which == "c1":
-    xg, yg, zg, ne, te, b, r_record, s_arr, start = synthetic.los_sampler_case(256, 256, 128, seed=0)
+    xg, yg, zg, ne, te, b, r_record, s_arr, start = cases.los_sampler_case(256, 256, 128, seed=0)
     ses.set_field_cubes(xg, yg, zg, ne, te, b)
     ses.sample(r_record, s_arr, start, 6.957e10)
     ses.sample(r_record, s_arr, start, 6.957e10)

@@ -21,6 +21,8 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))     # cases.los_sampler_case: the reference benchmark's fixture
+import cases  # noqa: E402
 from raytracinggrff_b200 import RaySession, synthetic  # noqa: E402
 
 HBM = json.load(open(ROOT / "MEASURED_PEAKS.json"))["hbm_gbs"] if (ROOT / "MEASURED_PEAKS.json").exists() else 6650.0
@@ -52,7 +54,7 @@ def run_all(ses, quick=False, with_cube_builder=True):
             ses.ctx.set_pipeline(True)
 
     # ---- C1 sampler -------------------------------------------------------------------------
-    args = synthetic.los_sampler_case(256, 256, 128, seed=0)
+    args = cases.los_sampler_case(256, 256, 128, seed=0)
     xg, yg, zg, ne, te, b, r_record, s_arr, start = args
     ses.set_field_cubes(xg, yg, zg, ne, te, b)
     n = r_record.shape[0] * r_record.shape[1]

@@ -58,7 +58,7 @@ def main():
         np.savez_compressed(out / f"sampler_fixture_seed{seed}.npz", **o)
 
     # config-1 shape at reduced size, real r_sun_cm
-    xg, yg, zg, ne, te, b, r_record, s_arr, ray_start = synthetic.los_sampler_case(24, 48, 40, seed=0)
+    xg, yg, zg, ne, te, b, r_record, s_arr, ray_start = cases.los_sampler_case(24, 48, 40, seed=0)
     o = sample_model_with_rays("cpu", xg, yg, zg, ne, te, b, r_record, s_arr, ray_start, r_sun_cm=6.957e10)
     np.savez_compressed(out / "sampler_c1_small.npz", **o)
 

@@ -165,7 +165,7 @@ def test_chunked_host_pipelines_match_the_oracle(oracle, session):
     """rtgrff_sample / rtgrff_get_mw_slice move large host arrays in chunks through pinned bounce buffers
     while earlier chunks compute; the results are those of the oracle (bit for bit for the sampler) —
     including ds, which looks back across chunk boundaries for the previous valid record."""
-    args = list(synthetic.los_sampler_case(160, 200, 64, seed=3))       # 25 600 rays x 200 records = 169 MB moved
+    args = list(cases.los_sampler_case(160, 200, 64, seed=3))       # 25 600 rays x 200 records = 169 MB moved
     s_arr = args[7].copy()
     s_arr[::3, ::5] = 0.0
     s_arr[40:75, 1::2] = np.nan          # long invalid runs: ds reaches back over many records

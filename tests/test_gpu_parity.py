@@ -173,7 +173,7 @@ def test_sampler_matches_reference_fixture(oracle, golden, seed):
 def test_sampler_config1_full_size(oracle):
     """BASELINE config 1 at full size: 65 536 rays x 256 samples, 128^3 cube."""
     from raytracinggrff_b200 import sample_model_with_rays
-    args = synthetic.los_sampler_case(256, 256, 128, seed=0)
+    args = cases.los_sampler_case(256, 256, 128, seed=0)
     gpu = sample_model_with_rays("cuda", *args, r_sun_cm=6.957e10)
     cpu = oracle.sample_model_with_rays_cpu(*args, r_sun_cm=6.957e10)
     for k in ("ne", "te", "b", "valid_mask"):

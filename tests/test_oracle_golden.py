@@ -45,7 +45,7 @@ def test_oracle_sampler_matches_reference_fixture(oracle, golden, seed):
 
 
 def test_oracle_sampler_c1_and_traced_paths(oracle, golden):
-    args = synthetic.los_sampler_case(24, 48, 40, seed=0)
+    args = cases.los_sampler_case(24, 48, 40, seed=0)
     out = oracle.sample_model_with_rays_cpu(*args, r_sun_cm=6.957e10)
     g = golden("sampler_c1_small")
     for k in ("ne", "te", "b", "ds", "valid_mask"):
