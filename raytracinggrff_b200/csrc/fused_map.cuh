@@ -38,6 +38,10 @@ struct FreqDev {
 #endif
 constexpr int kMaxFreqPerLaunch = RT_FREQ_PER_LAUNCH;
 
+#ifndef RT_PREFETCH
+#define RT_PREFETCH 0     // 1: L1 prefetch of the sampler's lines one step ahead (A/B)
+#endif
+
 struct MapArgs {
     RayCube cube;
     const float4 *fcube, *bcube;
@@ -188,6 +192,30 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_MINB) render_map_kernel(const Map
     bool tail_done = !has_ray;            // a frozen ray repeats the same record: ds = 0 -> empty voxel
 
     for (int i = 0; i < n_steps; ++i) {
+#if RT_PREFETCH
+        // the record taken after this step samples the field cubes in (or next to) the cell the ray is in now: ask L1
+        // for those lines a whole step ahead (with a record at every step they are still there from the last one)
+        if (stride > 1 && i == next_rec && alive) {
+            int ci, cj, ck;
+            float ftx, fty, ftz;
+            if (cell_of(a.fg, (float)s.rx, (float)s.ry, (float)s.rz, ci, cj, ck, ftx, fty, ftz)) {
+                const size_t sy = (size_t)a.fg.nz, sx = (size_t)a.fg.ny * a.fg.nz;
+                const size_t off = (size_t)ci * sx + (size_t)cj * sy + (size_t)ck;
+                const float4 *p0 = a.fcube + off;
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(p0));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(p0 + sy));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(p0 + sx));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(p0 + sx + sy));
+                if (BVEC) {
+                    const float4 *p1 = a.bcube + off;
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(p1));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(p1 + sy));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(p1 + sx));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(p1 + sx + sy));
+                }
+            }
+        }
+#endif
         if (alive) {
             const bool want_s = CS && (i == next_rec || a.cs_every_step || cumulative);
             alive = advance_ray<CS, MODE>(C, K, cache, s, fp.dt, a.perturb_ratio, want_s, s_step);

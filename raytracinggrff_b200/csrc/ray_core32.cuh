@@ -35,6 +35,9 @@
 #ifndef RT_PACK_TAIL
 #define RT_PACK_TAIL 1
 #endif
+#ifndef RT_UNROLL_Q
+#define RT_UNROLL_Q 0     // 1: the three rays of a pencil step as three inlined copies of the RK4 (A/B)
+#endif
 
 namespace rtgrff {
 
@@ -330,7 +333,11 @@ __device__ __forceinline__ bool step32(const RayCube &C, const StepConst &K, Cel
     float tx = 0.0f, ty = 0.0f, tz = 0.0f, e2x = 0.0f, e2y = 0.0f, e2z = 0.0f, eps = 0.0f;
     float d1x = 0.0f, d1y = 0.0f, d1z = 0.0f;
     bool moved = false;
+#if RT_UNROLL_Q
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
     for (int q = 0; q < n_rays; ++q) {
         const float2 qxy = __fmul2_rn(oxy, ixy);                      // start of this ray relative to p, cells
         const float qz = oz * K.iz;

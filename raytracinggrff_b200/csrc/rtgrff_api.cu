@@ -1172,10 +1172,15 @@ int rtgrff_render_map(rtgrff_ctx *c, int64_t n_rays, const double *x_start, cons
     const int variant = (trace_cs ? 8 : 0) | (voxel_order == RTGRFF_ORDER_REVERSED ? 4 : 0) | (use_bvec ? 2 : 0) | (gr ? 1 : 0);
 #define RT_MAP_CASE(v, CS, ORD, BV, GR)                                                                  \
     case v:                                                                                              \
-        if (mode == MODE_FAST32) render_map_kernel<CS, ORD, BV, GR, MODE_FAST32><<<grid, block, 0, c->stream>>>(a); \
-        else render_map_kernel<CS, ORD, BV, GR, MODE_F64><<<grid, block, 0, c->stream>>>(a);             \
+        if (mode == MODE_FAST32) {                                                                       \
+            if (carve >= 0) cudaFuncSetAttribute(render_map_kernel<CS, ORD, BV, GR, MODE_FAST32>,        \
+                                                 cudaFuncAttributePreferredSharedMemoryCarveout, carve);  \
+            render_map_kernel<CS, ORD, BV, GR, MODE_FAST32><<<grid, block, 0, c->stream>>>(a);           \
+        } else render_map_kernel<CS, ORD, BV, GR, MODE_F64><<<grid, block, 0, c->stream>>>(a);           \
         break;
     int mode = trace_variant() == 0 ? MODE_FAST32 : MODE_F64;
+    // the per-ray kernels use no shared memory: ask for the whole unified array as L1 (RTGRFF_CARVEOUT=-1 leaves the default)
+    static const int carve = getenv("RTGRFF_CARVEOUT") ? atoi(getenv("RTGRFF_CARVEOUT")) : 0;
     for (int f = 0; f < n_freq; ++f)
         if (!(max_stage_offset_cells(freqs[f].dt, trace_cs ? perturb_ratio : 0.0, c->wgeom.idx, c->wgeom.idy,
                                      c->wgeom.idz) < kMaxStageOffsetCells))
