@@ -299,9 +299,10 @@ def config_dict(w, args):
 
 
 def lib_fingerprint():
-    """sha1 of the kernel sources: ties a bench line to the ncu captures under profiles/."""
+    """sha1 of the kernel sources (csrc/*.cuh; the .cu file is host staging): ties a bench line to the ncu captures
+    under profiles/."""
     h = hashlib.sha1()
-    for p in sorted((ROOT / "raytracinggrff_b200" / "csrc").glob("*")):
+    for p in sorted((ROOT / "raytracinggrff_b200" / "csrc").glob("*.cuh")):
         h.update(p.read_bytes())
     return h.hexdigest()[:12]
 

@@ -3,6 +3,7 @@
 #include <stdarg.h>
 
 #include <algorithm>
+#include <condition_variable>
 #include <mutex>
 #include <new>
 #include <thread>
@@ -153,26 +154,87 @@ static int host_threads()
     return v;
 }
 
-// memcpy split over a few threads (one thread saturates neither the memory channels nor, for fresh
-// numpy output arrays, the page-fault path)
+// memcpy split over a few persistent worker threads (one thread saturates neither the memory channels nor,
+// for fresh numpy output arrays, the page-fault path; spawning threads per copy costs as much as a small copy)
+class CopyPool {
+public:
+    explicit CopyPool(int n)
+    {
+        for (int t = 0; t < n; ++t) workers_.emplace_back([this] { run(); });
+    }
+    ~CopyPool()
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto &t : workers_) t.join();
+    }
+    int size() const { return (int)workers_.size(); }
+    // the calling thread takes a share too and returns when every piece is done
+    void copy(void *dst, const void *src, size_t bytes, int parts)
+    {
+        const size_t per = ((bytes / parts) + 4095) & ~(size_t)4095;
+        int posted = 0;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            for (int t = 1; t < parts; ++t) {
+                const size_t o = per * t;
+                if (o >= bytes) break;
+                tasks_.push_back(Task{(char *)dst + o, (const char *)src + o, std::min(per, bytes - o)});
+                ++posted;
+            }
+            pending_ += posted;
+        }
+        cv_.notify_all();
+        memcpy(dst, src, std::min(per, bytes));
+        std::unique_lock<std::mutex> lk(mu_);
+        done_.wait(lk, [this] { return pending_ == 0; });
+    }
+
+private:
+    struct Task { char *dst; const char *src; size_t len; };
+    void run()
+    {
+        for (;;) {
+            Task t;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [this] { return stop_ || !tasks_.empty(); });
+                if (stop_ && tasks_.empty()) return;
+                t = tasks_.back();
+                tasks_.pop_back();
+            }
+            memcpy(t.dst, t.src, t.len);
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (--pending_ == 0) done_.notify_all();
+            }
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::vector<Task> tasks_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    int pending_ = 0;
+    bool stop_ = false;
+};
+
+static std::mutex g_copy_mu;      // one copy at a time through the pool (contexts of several host threads share it)
+
 static void parallel_copy(void *dst, const void *src, size_t bytes)
 {
     const int nt = host_threads();
-    if (nt <= 1 || bytes < ((size_t)2 << 20)) {
+    // at least 2 MB per thread: below that the hand-over costs more than it saves
+    const int parts = (int)std::min<size_t>((size_t)nt, bytes / ((size_t)2 << 20));
+    if (parts <= 1) {
         memcpy(dst, src, bytes);
         return;
     }
-    const size_t per = ((bytes / nt) + 4095) & ~(size_t)4095;
-    std::vector<std::thread> th;
-    th.reserve(nt);
-    for (int t = 1; t < nt; ++t) {
-        const size_t o = per * t;
-        if (o >= bytes) break;
-        const size_t len = std::min(per, bytes - o);
-        th.emplace_back([=] { memcpy((char *)dst + o, (const char *)src + o, len); });
-    }
-    memcpy(dst, src, std::min(per, bytes));
-    for (auto &t : th) t.join();
+    static CopyPool *pool = new CopyPool(nt - 1);      // lives for the process: workers sleep on a condition variable
+    std::lock_guard<std::mutex> lk(g_copy_mu);
+    pool->copy(dst, src, bytes, parts);
 }
 
 static int pin_reserve(rtgrff_ctx *c, int idx, size_t bytes)
