@@ -197,7 +197,51 @@ def check_s_input_scales_the_source(get_mw):
     np.testing.assert_allclose(run(get_mw, P, nu)[5:], Sk.mean() * base[5:], rtol=1e-5)
 
 
-ALL_CHECKS = [check_s_input_scales_the_source, check_frequency_grid_and_codes, check_optically_thick_isothermal, check_optically_thin_free_free,
+def check_literature_numbers(get_mw):
+    """Anchors OUTSIDE this repo's own restatement: the closed-form approximations of the literature with their
+    PUBLISHED numerical constants (not the constants of oracle_grff.c), in the regimes where they hold.
+      * free-free: Dulk (1985, ARA&A 23, 169) eqs. 20-21: kappa = 9.78e-3 n_e^2 / (nu^2 T^1.5) x (18.2 + ln T^1.5 - ln nu)
+        for T < 2e5 K, x (24.5 + ln T - ln nu) above, for a hydrogen plasma: the implementation carries sum(Z^2 n_i)/n_e
+        for H + He (1.145) on top and 24.573 for 24.5.
+      * gyroresonance: White & Kundu (1997, Sol. Phys. 174, 31) eq. 1 / Dulk (1985) eq. 36:
+        tau_{X,O} = 0.0133 n_e L_B / nu x (s^2 / s!) (s^2 sin^2 theta / (2 mu))^(s-1) (1 -+ sigma |cos theta|)^2,
+        mu = m c^2 / k T = 5.93e9 / T, valid for quasi-circular modes and nu >> nu_p.
+    Agreement is expected to the accuracy of those approximations (a percent or a few), not to rounding."""
+    to_sfu = AREA / AU ** 2 / 1e-19
+    # --- free-free, both Coulomb-logarithm branches, optically thin, nu >> nu_p
+    for T in (5.0e4, 2.0e6):
+        ne, nu, dz = 1.0e8, 5.0e9, 1.0e8
+        RL = run(get_mw, parms(1, dz, T, ne, 0.0), nu)
+        src = nu * nu * KB * T / (C * C)                                  # n ~ 1
+        tau = (RL[5, 0] + RL[6, 0]) / to_sfu / (2 * src)
+        coul = 18.2 + 1.5 * np.log(T) - np.log(nu) if T < 2e5 else 24.5 + np.log(T) - np.log(nu)
+        tau_dulk = 9.78e-3 * ne * ne / (nu * nu * T ** 1.5) * coul * dz
+        assert tau < 1e-3
+        np.testing.assert_allclose(tau / ZETA, tau_dulk, rtol=6e-3)      # He correction apart: within 0.6 %
+    # --- gyroresonance, s = 2 and 3, theta = 40 deg (quasi-circular: u sin^4 / (4 cos^2) << 1), FF off, layers thin
+    for s, fact, ne in ((2, 2.0, 2.0e4), (3, 6.0, 5.0e6)):
+        nu, T, dz, theta = 5.0e9, 3.0e6, 2.0e8, 40.0
+        Bres = nu / (2.80e6 * s)                                            # nu_B = 2.80 MHz per gauss
+        lo = {2: 0.80, 3: 0.95}[s]                                          # keeps the neighbouring harmonics out
+        Bp, Bk = 1.08 * Bres, lo * Bres
+        RL = run(get_mw, parms(2, dz, T, ne, [Bp, Bk], theta, flag=2 + 4), nu)
+        th = np.radians(theta)
+        LB = Bres * dz / abs(Bk - Bp)
+        mu = 5.93e9 / T
+        src = nu * nu * KB * T / (C * C)
+        tau, tau_wk = {}, {}
+        for row, sigma in ((6, -1), (5, +1)):                               # X (sigma = -1) is R for theta < 90
+            tau[sigma] = -np.log1p(-RL[row, 0] / to_sfu / src)
+            tau_wk[sigma] = (0.0133 * ne * LB / nu * (s * s / fact) * (s * s * np.sin(th) ** 2 / (2 * mu)) ** (s - 1)
+                             * (1 - sigma * abs(np.cos(th))) ** 2)
+        assert 0.02 < tau[-1] < 0.3
+        np.testing.assert_allclose(tau[-1], tau_wk[-1], rtol=0.02)          # X mode: the published number to 2 %
+        # O mode: the (1 - |cos|)^2 factor of the quasi-circular approximation is known to overestimate it; the exact
+        # polarisation coefficients used here give a few times less — bounded, and far below the X mode
+        assert tau_wk[+1] / 6 < tau[+1] < tau_wk[+1] and tau[+1] < 0.05 * tau[-1]
+
+
+ALL_CHECKS = [check_literature_numbers, check_s_input_scales_the_source, check_frequency_grid_and_codes, check_optically_thick_isothermal, check_optically_thin_free_free,
               check_polarisation_sign_and_magnitude, check_cutoff_blocks_background, check_mode_coupling_limits,
               check_gyroresonance_layer]
 
