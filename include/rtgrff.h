@@ -49,6 +49,10 @@ int rtgrff_ctx_create_on_stream(int device, void *stream, rtgrff_ctx **out);
 int rtgrff_current_device(void);
 int rtgrff_ctx_destroy(rtgrff_ctx *ctx);
 int rtgrff_ctx_synchronize(rtgrff_ctx *ctx);
+/* The per-ray kernels (rtgrff_render_map, rtgrff_emission_traced) evaluate a voxel's opacities in float32 where that
+ * is well conditioned and in FP64 near the mode cut-offs.  enabled = 1 forces FP64 for every voxel
+ * (default 0; env RTGRFF_GRFF64=1): A/B and validation switch.  PyGET_MW / rtgrff_get_mw_slice are always FP64. */
+int rtgrff_ctx_set_grff64(rtgrff_ctx *ctx, int enabled);
 /* Large host arrays travel in chunks through page-locked bounce buffers, overlapped with the kernels
  * (rtgrff_sample, rtgrff_get_mw_slice, cube uploads, image download).  enabled = 0 switches to one plain copy
  * each way, so that rtgrff_ctx_last_kernel_ms brackets the kernel alone (default 1; env RTGRFF_PIPELINE=0). */

@@ -39,7 +39,7 @@ EXPORTS = (
     "rtgrff_ctx_create_on_stream", "rtgrff_current_device", "rtgrff_get_mw_slice_device", "rtgrff_memcpy",
     "rtgrff_export_cubes", "rtgrff_shard_rows", "rtgrff_comm_unique_id", "rtgrff_comm_init_rank",
     "rtgrff_comm_destroy", "rtgrff_gather_image", "rtgrff_device_alloc", "rtgrff_device_free",
-    "rtgrff_ctx_set_pipeline",
+    "rtgrff_ctx_set_pipeline", "rtgrff_ctx_set_grff64",
 )
 
 
@@ -70,6 +70,7 @@ def load():
     lib.rtgrff_current_device.restype = c_int
     lib.rtgrff_get_mw_slice_device.argtypes = [c_void_p, ip, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.rtgrff_ctx_set_pipeline.argtypes = [c_void_p, c_int]
+    lib.rtgrff_ctx_set_grff64.argtypes = [c_void_p, c_int]
     lib.rtgrff_device_alloc.argtypes = [c_void_p, POINTER(c_void_p), ctypes.c_size_t]
     lib.rtgrff_device_free.argtypes = [c_void_p, c_void_p]
     lib.rtgrff_memcpy.argtypes = [c_void_p, c_void_p, c_void_p, ctypes.c_size_t, c_int]
@@ -253,6 +254,10 @@ class Context:
 
     def synchronize(self):
         check(self._lib.rtgrff_ctx_synchronize(self.handle))
+
+    def set_grff64(self, enabled):
+        """FP64 voxel evaluation in the per-ray kernels on / off (rtgrff_ctx_set_grff64)."""
+        check(self._lib.rtgrff_ctx_set_grff64(self.handle, int(bool(enabled))))
 
     def set_pipeline(self, enabled):
         """Chunked pinned host pipelines on / off (rtgrff_ctx_set_pipeline)."""

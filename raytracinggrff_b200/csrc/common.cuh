@@ -85,6 +85,7 @@ struct rtgrff_ctx {
     bool own_stream = false;
     // second stream + events + pinned bounce buffers of the chunked host<->device pipelines
     // (rtgrff_sample, rtgrff_get_mw_slice): host pack / H2D / kernel / D2H / host unpack overlap
+    int grff64 = 0;                  // per-ray kernels evaluate every voxel in FP64 (RTGRFF_GRFF64, rtgrff_ctx_set_grff64)
     int pipeline = 1;                // chunked pinned host pipelines on (RTGRFF_PIPELINE, rtgrff_ctx_set_pipeline)
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t chunk_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // in[2], kernel[2], out[2]

@@ -416,6 +416,7 @@ static int ctx_create(int device, void *stream, bool caller_stream, rtgrff_ctx *
     if (!c) return fail(RTGRFF_ENOMEM, "out of host memory");
     c->device = device;
     c->pipeline = pipeline_default();
+    c->grff64 = grff64();
     cudaError_t e = cudaSuccess;
     cudaDeviceProp prop;
     if ((e = cudaGetDeviceProperties(&prop, device)) == cudaSuccess) {
@@ -494,6 +495,13 @@ int rtgrff_ctx_synchronize(rtgrff_ctx *c)
 {
     RT_USE(c);
     RT_CUDA(cudaStreamSynchronize(c->stream));
+    return RTGRFF_OK;
+}
+
+int rtgrff_ctx_set_grff64(rtgrff_ctx *c, int enabled)
+{
+    if (!c) return fail(RTGRFF_EINVAL, "null context");
+    c->grff64 = enabled ? 1 : 0;
     return RTGRFF_OK;
 }
 
@@ -1137,7 +1145,7 @@ int rtgrff_emission_traced(rtgrff_ctx *c, double pixel_area_cm2, double freq0_hz
     a.n_rec = c->smp_n; a.n_rays = c->smp_rays;
     a.area = pixel_area_cm2; a.freq0 = freq0_hz; a.log_step = freq_log_step;
     a.n_freq = n_freq; a.em_flag = em_flag; a.s_max = s_max;
-    a.grff64 = grff64();
+    a.grff64 = c->grff64;
     a.tb = c->out0.as<double>(); a.vi = c->out1.as<double>();
     RT_CUDA(cudaEventRecord(c->ev0, c->stream));
     emission_rays_kernel<<<blocks_for((int64_t)n, 128), 128, 0, c->stream>>>(a);
@@ -1225,7 +1233,7 @@ int rtgrff_render_map(rtgrff_ctx *c, int64_t n_rays, const double *x_start, cons
     a.em_flag = em_flag; a.s_max = s_max; a.use_bvec = use_bvec; a.order = voxel_order;
     a.cs_every_step = cs_every_step();
     a.s_mode = s_mode; a.s_input = s_input_on ? 1 : 0;
-    a.grff64 = grff64();
+    a.grff64 = c->grff64;
     a.tb = dtb; a.vi = dvi;
     a.active_steps = c->counters.as<unsigned long long>();
     const dim3 block(RT_BLOCK);

@@ -56,6 +56,11 @@ class RaySession:
         self.traced_cs = False
 
     def close(self):
+        for ptr_, _ in self.__dict__.pop("_scratch", {}).values():
+            try:
+                self._lib.rtgrff_device_free(self.ctx.handle, ctypes.c_void_p(ptr_))
+            except Exception:      # the context may be gone already
+                pass
         self.ctx.close()
 
     def __enter__(self):

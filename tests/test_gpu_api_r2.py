@@ -272,3 +272,37 @@ def test_workers_split_rays_over_gpus_without_changing_the_map(backend):
     assert (one["emission_cube"] > 0).mean() > 0.3
     assert np.array_equal(one["emission_cube"], many["emission_cube"])
     assert np.array_equal(one["emission_polVI_cube"], many["emission_polVI_cube"])
+
+
+def test_fp32_voxel_path_against_forced_fp64(session):
+    """The float32 voxel evaluation of the per-ray kernels (csrc/grff_fast.cuh) against the same kernels with every
+    voxel forced through FP64, on maps where the cut-offs matter: low frequencies (rays turn where v -> 1, the
+    voxels around the turning point take the FP64 fallback) and GHz frequencies over the active region (strong B:
+    X-mode cut-off, gyro-resonance guard).  Both the fused and the staged (emission_traced) consumers."""
+    c = synthetic.corona_cube(96, 3.0, active_region=True)
+    g3 = (c["x_grid"], c["y_grid"], c["z_grid"])
+    session.set_omega_cube(c["omega_pe"], *g3)
+    session.set_field_cubes(*g3, c["ne"], c["te"], c["b"], c["bx"], c["by"], c["bz"])
+    n = 24
+    xs, ys, zs, kv = synthetic.ray_launch_geometry(n, 1.3, 3.0)
+    area = (2 * 1.3 / n * 6.957e10) ** 2
+    fps = [dict(freq_hz=f, **synthetic.frequency_scaled_params(f)) for f in (40e6, 150e6, 1.2e9)]
+    out = {}
+    try:
+        for mode in (0, 1):
+            session.ctx.set_grff64(mode)
+            tb, vi, _ = session.render_map(xs, ys, zs, fps, pixel_area_cm2=area, em_flag=4, use_bvec=True)
+            p = fps[1]
+            session.trace(p["freq_hz"], xs, ys, zs, kv, p["dt"], p["n_steps"], p["record_stride"], True, 2.0, fetch=False)
+            session.sample_traced(np.column_stack([xs, ys, zs]), 6.957e10, fetch=False)
+            tb_s, vi_s = session.emission_traced(area, p["freq_hz"])
+            out[mode] = (tb, vi, tb_s, vi_s)
+    finally:
+        session.ctx.set_grff64(0)
+    for a, b in ((out[0][0], out[1][0]), (out[0][2], out[1][2])):
+        on = b != 0
+        assert on.mean() > 0.3 and np.array_equal(a != 0, on)
+        rel = np.abs(a[on] - b[on]) / b[on]
+        assert rel.max() < 2e-5, rel.max()
+    assert np.abs(out[0][1] - out[1][1]).max() < 2e-5 and np.abs(out[0][3] - out[1][3]).max() < 2e-5
+    assert not np.array_equal(out[0][0], out[1][0])          # the two paths are different arithmetic

@@ -224,11 +224,20 @@ def test_sample_traced_equals_host_round_trip(oracle, golden, session):
     host = session.sample(r, s, ray_start, 6.957e10)
     for k in ("ne", "te", "b", "ds", "valid_mask", "s"):
         assert np.array_equal(dev[k], host[k], equal_nan=True), k
-    # and against the oracle fed the oracle's own paths (differences only through |dr| <= 1e-5)
+    # the oracle's sampler on the GPU's own paths: bit for bit
+    orc = oracle.sample_model_with_rays_cpu(c["x_grid"], c["y_grid"], c["z_grid"], c["ne"], c["te"], c["b"], r, s,
+                                            ray_start, 6.957e10)
+    for k in ("ne", "te", "b", "valid_mask"):
+        assert np.array_equal(dev[k], orc[k], equal_nan=True), k
+    np.testing.assert_allclose(dev["ds"], orc["ds"], rtol=1e-6, atol=0)
+    # and against the reference's sampler on the reference's own paths (golden): the two path sets differ by
+    # |dr| <= 1e-5 R_sun, so validity can only flip on the record at which a ray leaves the cube and the sampled
+    # density moves by |grad ln n_e| |dr| (< 1e-4 on this cube)
     g = golden("sampler_on_traced_paths")
-    assert np.mean(dev["valid_mask"] == g["valid_mask"]) > 0.999
+    flips = dev["valid_mask"] != g["valid_mask"]
+    assert flips.mean() < 1e-3 and flips.sum(axis=0).max() <= 2
     both = dev["valid_mask"] & g["valid_mask"]
-    np.testing.assert_allclose(dev["ne"][both], g["ne"][both], rtol=2e-3)
+    np.testing.assert_allclose(dev["ne"][both], g["ne"][both], rtol=2e-4)
 
 
 # ------------------------------------------------------------------------------------ GRFF ----
