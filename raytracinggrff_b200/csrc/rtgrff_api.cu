@@ -226,8 +226,9 @@ static std::mutex g_copy_mu;      // one copy at a time through the pool (contex
 static void parallel_copy(void *dst, const void *src, size_t bytes)
 {
     const int nt = host_threads();
-    // at least 2 MB per thread: below that the hand-over costs more than it saves
-    const int parts = (int)std::min<size_t>((size_t)nt, bytes / ((size_t)2 << 20));
+    // at least 256 KB per thread: the workers are persistent, the hand-over is a condition-variable wake-up, and the
+    // unpack into fresh numpy arrays is bound by page faults per thread, so it wants every thread it can get
+    const int parts = (int)std::min<size_t>((size_t)nt, bytes / ((size_t)256 << 10));
     if (parts <= 1) {
         memcpy(dst, src, bytes);
         return;
