@@ -39,8 +39,6 @@ struct GridGeomF {
     float x0, y0, z0;
     float idx, idy, idz;
     float fxl, fyl, fzl;   // (float)(n - 1): the in-bounds test 0 <= f <= n-1 of gpu_raytrace.py:505-511
-    int cm;                // 1: the cube pointers handed to the sampler are CELL-MAJOR copies (8 corners = one
-                           // 128-byte line per cell, los_sampler.cuh), 0: node cubes
 };
 
 extern thread_local char g_err[512];
@@ -109,8 +107,6 @@ struct rtgrff_ctx {
 
     // field cubes {ne, te, |B|, 0} and {bx, by, bz, 0}
     rtgrff::DevBuf fcube, bcube;
-    rtgrff::DevBuf fcell, bcell;     // cell-major copies of the two (8 float4 per cell), built when they fit
-    bool has_fcell = false, has_bcell = false;
     rtgrff::GridGeom fgeom{};
     rtgrff::GridGeomF fgeomf{};
     bool has_fcube = false, has_bvec = false;

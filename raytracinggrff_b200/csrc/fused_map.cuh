@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_MINB) render_map_kernel(const Map
 #if RT_PREFETCH
         // the record taken after this step samples the field cubes in (or next to) the cell the ray is in now: ask L1
         // for those lines a whole step ahead (with a record at every step they are still there from the last one)
-        if (stride > 1 && i == next_rec && alive && !a.fg.cm) {
+        if (stride > 1 && i == next_rec && alive) {
             int ci, cj, ck;
             float ftx, fty, ftz;
             if (cell_of(a.fg, (float)s.rx, (float)s.ry, (float)s.rz, ci, cj, ck, ftx, fty, ftz)) {

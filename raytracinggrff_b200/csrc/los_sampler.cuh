@@ -49,18 +49,6 @@ __device__ __forceinline__ float2 lerp_np2(float2 a, float2 b, float2 u, float2 
     return __fadd2_rn(__fmul2_rn(a, u), __fmul2_rn(b, t));
 }
 
-// The 8 corners of cell `off` (node-cube element offset of its (i,j,k) corner).  Node cube: four 32-byte runs
-// in four different rows (up to 8 lines per warp-wide gather of neighbouring rays, 4 x 32 for unrelated ones);
-// cell-major copy (g.cm, build_cell_cube_kernel): the 8 corners are one aligned 128-byte line.  Same values
-// either way, so the arithmetic that follows is unchanged (bit-exact with numpy where it was).
-#define RT_LOAD_CORNERS(cube, g, off)                                                                         \
-    const size_t sy_ = (size_t)(g).nz, sx_ = (size_t)(g).ny * (g).nz;                                         \
-    const float4 *p_ = (g).cm ? (cube) + (off) * 8 : (cube) + (off);                                          \
-    const size_t o2_ = (g).cm ? 2 : sy_, o3_ = (g).cm ? 3 : sy_ + 1, o4_ = (g).cm ? 4 : sx_,                   \
-                 o5_ = (g).cm ? 5 : sx_ + 1, o6_ = (g).cm ? 6 : sx_ + sy_, o7_ = (g).cm ? 7 : sx_ + sy_ + 1;   \
-    const float4 c000 = __ldg(p_), c001 = __ldg(p_ + 1), c010 = __ldg(p_ + o2_), c011 = __ldg(p_ + o3_);      \
-    const float4 c100 = __ldg(p_ + o4_), c101 = __ldg(p_ + o5_), c110 = __ldg(p_ + o6_), c111 = __ldg(p_ + o7_);
-
 #define RT_TRI_NP(m)                                                                              \
     lerp_np(lerp_np(lerp_np(c000.m, c100.m, tx), lerp_np(c010.m, c110.m, tx), ty),                \
             lerp_np(lerp_np(c001.m, c101.m, tx), lerp_np(c011.m, c111.m, tx), ty), tz)
@@ -77,8 +65,11 @@ __device__ __forceinline__ FieldSample sample_fields(const float4 *__restrict__ 
         o.ne = fill_ne; o.te = fill_te; o.b = fill_b;
         return o;
     }
-    const size_t off = ((size_t)i * g.ny + (size_t)j) * g.nz + (size_t)k;
-    RT_LOAD_CORNERS(cube, g, off)
+    const size_t sy = (size_t)g.nz, sx = (size_t)g.ny * g.nz;
+    const float4 *p = cube + ((size_t)i * sx + (size_t)j * sy + (size_t)k);
+    const float4 c000 = __ldg(p), c001 = __ldg(p + 1), c010 = __ldg(p + sy), c011 = __ldg(p + sy + 1);
+    const float4 c100 = __ldg(p + sx), c101 = __ldg(p + sx + 1), c110 = __ldg(p + sx + sy),
+                 c111 = __ldg(p + sx + sy + 1);
     // nesting order of the reference: x first, then y, then z (gpu_raytrace.py:528-534)
     o.ne = RT_TRI_NP(x);
     o.te = RT_TRI_NP(y);
@@ -102,7 +93,8 @@ __device__ __forceinline__ FieldSample sample_fields_bvec(const float4 *__restri
         o.ne = fill_ne; o.te = fill_te; o.b = fill_b;
         return o;
     }
-    const size_t off = ((size_t)i * g.ny + (size_t)j) * g.nz + (size_t)k;
+    const size_t sy = (size_t)g.nz, sx = (size_t)g.ny * g.nz;
+    const size_t off = (size_t)i * sx + (size_t)j * sy + (size_t)k;
     const float2 tx2 = make_float2(tx, tx), ux2 = make_float2(__fsub_rn(1.0f, tx), __fsub_rn(1.0f, tx));
     const float2 ty2 = make_float2(ty, ty), uy2 = make_float2(__fsub_rn(1.0f, ty), __fsub_rn(1.0f, ty));
     const float2 tz2 = make_float2(tz, tz), uz2 = make_float2(__fsub_rn(1.0f, tz), __fsub_rn(1.0f, tz));
@@ -112,13 +104,19 @@ __device__ __forceinline__ FieldSample sample_fields_bvec(const float4 *__restri
     lerp_np2(lerp_np2(lerp_np2(H(c000), H(c100), ux2, tx2), lerp_np2(H(c010), H(c110), ux2, tx2), uy2, ty2),  \
              lerp_np2(lerp_np2(H(c001), H(c101), ux2, tx2), lerp_np2(H(c011), H(c111), ux2, tx2), uy2, ty2), uz2, tz2)
     {
-        RT_LOAD_CORNERS(fcube, g, off)
+        const float4 *p = fcube + off;
+        const float4 c000 = __ldg(p), c001 = __ldg(p + 1), c010 = __ldg(p + sy), c011 = __ldg(p + sy + 1);
+        const float4 c100 = __ldg(p + sx), c101 = __ldg(p + sx + 1), c110 = __ldg(p + sx + sy),
+                     c111 = __ldg(p + sx + sy + 1);
         const float2 nt = RT_TRI_NP2(RT_LO);
         o.ne = nt.x; o.te = nt.y;
         o.b = RT_TRI_NP(z);
     }
     {
-        RT_LOAD_CORNERS(bcube, g, off)
+        const float4 *p = bcube + off;
+        const float4 c000 = __ldg(p), c001 = __ldg(p + 1), c010 = __ldg(p + sy), c011 = __ldg(p + sy + 1);
+        const float4 c100 = __ldg(p + sx), c101 = __ldg(p + sx + 1), c110 = __ldg(p + sx + sy),
+                     c111 = __ldg(p + sx + sy + 1);
         const float2 bxy = RT_TRI_NP2(RT_LO);
         bv.x = bxy.x; bv.y = bxy.y;
         bv.z = RT_TRI_NP(z);
@@ -148,7 +146,8 @@ __device__ __forceinline__ FieldSample sample_fields_bvec_fast(const float4 *__r
         o.ne = fill_ne; o.te = fill_te;
         return o;
     }
-    const size_t off = ((size_t)i * g.ny + (size_t)j) * g.nz + (size_t)k;
+    const size_t sy = (size_t)g.nz, sx = (size_t)g.ny * g.nz;
+    const size_t off = (size_t)i * sx + (size_t)j * sy + (size_t)k;
     const float2 tx2 = make_float2(tx, tx), ux2 = make_float2(__fsub_rn(1.0f, tx), __fsub_rn(1.0f, tx));
     const float2 ty2 = make_float2(ty, ty), uy2 = make_float2(__fsub_rn(1.0f, ty), __fsub_rn(1.0f, ty));
     const float2 tz2 = make_float2(tz, tz), uz2 = make_float2(__fsub_rn(1.0f, tz), __fsub_rn(1.0f, tz));
@@ -157,13 +156,19 @@ __device__ __forceinline__ FieldSample sample_fields_bvec_fast(const float4 *__r
     lerp_np2(lerp_np2(lerp_np2(H(c000), H(c100), ux2, tx2), lerp_np2(H(c010), H(c110), ux2, tx2), uy2, ty2),  \
              lerp_np2(lerp_np2(H(c001), H(c101), ux2, tx2), lerp_np2(H(c011), H(c111), ux2, tx2), uy2, ty2), uz2, tz2)
     {
-        RT_LOAD_CORNERS(fcube, g, off)
+        const float4 *p = fcube + off;
+        const float4 c000 = __ldg(p), c001 = __ldg(p + 1), c010 = __ldg(p + sy), c011 = __ldg(p + sy + 1);
+        const float4 c100 = __ldg(p + sx), c101 = __ldg(p + sx + 1), c110 = __ldg(p + sx + sy),
+                     c111 = __ldg(p + sx + sy + 1);
         const float2 nt = RT_TRI_NP2(RT_LO);
         o.ne = nt.x; o.te = nt.y;
     }
 #undef RT_TRI_NP2
     {
-        RT_LOAD_CORNERS(bcube, g, off)
+        const float4 *p = bcube + off;
+        const float4 c000 = __ldg(p), c001 = __ldg(p + 1), c010 = __ldg(p + sy), c011 = __ldg(p + sy + 1);
+        const float4 c100 = __ldg(p + sx), c101 = __ldg(p + sx + 1), c110 = __ldg(p + sx + sy),
+                     c111 = __ldg(p + sx + sy + 1);
 #define RT_FL2(a, b, t) __ffma2_rn(t, __fadd2_rn(b, make_float2(-(a).x, -(a).y)), a)
 #define RT_FL(a, b, t) fmaf(t, (b) - (a), a)
         const float2 bxy = RT_FL2(RT_FL2(RT_FL2(RT_LO(c000), RT_LO(c100), tx2), RT_FL2(RT_LO(c010), RT_LO(c110), tx2), ty2),
@@ -185,8 +190,11 @@ __device__ __forceinline__ float3 sample_bvec(const float4 *__restrict__ cube, c
     int i, j, k;
     float tx, ty, tz;
     if (!cell_of(g, px, py, pz, i, j, k, tx, ty, tz)) return make_float3(0.f, 0.f, 0.f);
-    const size_t off = ((size_t)i * g.ny + (size_t)j) * g.nz + (size_t)k;
-    RT_LOAD_CORNERS(cube, g, off)
+    const size_t sy = (size_t)g.nz, sx = (size_t)g.ny * g.nz;
+    const float4 *p = cube + ((size_t)i * sx + (size_t)j * sy + (size_t)k);
+    const float4 c000 = __ldg(p), c001 = __ldg(p + 1), c010 = __ldg(p + sy), c011 = __ldg(p + sy + 1);
+    const float4 c100 = __ldg(p + sx), c101 = __ldg(p + sx + 1), c110 = __ldg(p + sx + sy),
+                 c111 = __ldg(p + sx + sy + 1);
     return make_float3(RT_TRI_NP(x), RT_TRI_NP(y), RT_TRI_NP(z));
 }
 #undef RT_TRI_NP
@@ -304,23 +312,6 @@ __global__ void interleave3_kernel(const float *__restrict__ a, const float *__r
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n;
          q += (int64_t)gridDim.x * blockDim.x)
         out[q] = make_float4(a[q], b[q], c[q], 0.0f);
-}
-
-// Node cube -> cell-major cube: the 8 corners of cell (i,j,k) at [off*8, off*8+8), off = (i*ny + j)*nz + k, in
-// the order c000 c001 c010 c011 c100 c101 c110 c111 (z fastest) — one aligned 128-byte line per cell, 8x the
-// memory.  The entries of the last node of each axis stay unused (cell_of clips the cell index to n-2).
-__global__ void build_cell_cube_kernel(const float4 *__restrict__ nodes, float4 *__restrict__ cells, int nx, int ny, int nz)
-{
-    const int64_t nvox = (int64_t)nx * ny * nz;
-    const int sy = nz, sx = ny * nz;
-    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nvox; q += (int64_t)gridDim.x * blockDim.x) {
-        const int k = (int)(q % nz), j = (int)((q / nz) % ny), i = (int)(q / sx);
-        if (i >= nx - 1 || j >= ny - 1 || k >= nz - 1) continue;
-        const float4 *p = nodes + q;
-        float4 *o = cells + q * 8;
-        o[0] = p[0]; o[1] = p[1]; o[2] = p[sy]; o[3] = p[sy + 1];
-        o[4] = p[sx]; o[5] = p[sx + 1]; o[6] = p[sx + sy]; o[7] = p[sx + sy + 1];
-    }
 }
 
 // the inverse: one channel-interleaved cube -> three planar arrays (rtgrff_export_cubes)

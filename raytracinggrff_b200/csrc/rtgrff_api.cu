@@ -350,39 +350,6 @@ static int build_poly_cube(rtgrff_ctx *c, int nx, int ny, int nz)
     return RTGRFF_OK;
 }
 
-// Cell-major copies of the field cubes for the samplers (8 corners = one 128-byte line per cell, 8x the node
-// cube): built when each fits in a third of the free device memory (RTGRFF_CELL_CUBE=0 disables, =1 forces);
-// without them the samplers gather from the node cubes.
-static int build_cell_cubes(rtgrff_ctx *c, int nx, int ny, int nz)
-{
-    c->has_fcell = c->has_bcell = false;
-    const char *e = getenv("RTGRFF_CELL_CUBE");
-    if (e && e[0] == '0') return RTGRFF_OK;
-    const size_t bytes = (size_t)nx * ny * nz * 8 * sizeof(float4);
-    const unsigned int blocks = blocks_for((int64_t)nx * ny * nz, 256);
-    for (int pass = 0; pass < (c->has_bvec ? 2 : 1); ++pass) {
-        DevBuf &dst = pass ? c->bcell : c->fcell;
-        if (bytes > dst.cap && !(e && e[0] == '1')) {
-            size_t free_b = 0, total_b = 0;
-            if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || bytes > free_b / 3) return RTGRFF_OK;
-        }
-        RT_TRY(dst.reserve(bytes));
-        build_cell_cube_kernel<<<blocks, 256, 0, c->stream>>>((pass ? c->bcube : c->fcube).as<float4>(), dst.as<float4>(), nx, ny, nz);
-        RT_TRY(launched(c, "build_cell_cube_kernel"));
-        (pass ? c->has_bcell : c->has_fcell) = true;
-    }
-    return RTGRFF_OK;
-}
-
-// what the samplers read: the cell-major copies when all the cubes the call needs have one
-static void sampler_cubes(const rtgrff_ctx *c, bool need_bvec, const float4 *&f, const float4 *&b, GridGeomF &g)
-{
-    g = c->fgeomf;
-    const bool cm = c->has_fcell && (!need_bvec || c->has_bcell);
-    g.cm = cm ? 1 : 0;
-    f = (cm ? c->fcell : c->fcube).as<float4>();
-    b = need_bvec ? (cm ? c->bcell : c->bcube).as<float4>() : nullptr;
-}
 
 static int cs_every_step()
 {
@@ -505,7 +472,7 @@ int rtgrff_ctx_destroy(rtgrff_ctx *c)
     }
     DevBuf *bufs[] = {&c->wcube, &c->pcube, &c->fcube, &c->bcube, &c->rec_pos, &c->rec_s, &c->smp_ne, &c->smp_te, &c->smp_b,
                       &c->smp_ds, &c->smp_s, &c->smp_valid, &c->in0, &c->in1, &c->in2, &c->in3, &c->out0, &c->out1,
-                      &c->out2, &c->out3, &c->out4, &c->out5, &c->stage, &c->counters, &c->gather_buf, &c->image_buf, &c->fcell, &c->bcell};
+                      &c->out2, &c->out3, &c->out4, &c->out5, &c->stage, &c->counters, &c->gather_buf, &c->image_buf};
     for (DevBuf *b : bufs) b->release();
     for (DevBuf &b : c->slot) b.release();
     c->slot_grids.release();
@@ -620,8 +587,6 @@ int rtgrff_set_field_cubes(rtgrff_ctx *c, const float *ne, const float *te, cons
     f.fxl = (float)(nx - 1); f.fyl = (float)(ny - 1); f.fzl = (float)(nz - 1);
     c->has_fcube = true;
     c->has_bvec = bvec;
-    f.cm = 0;
-    RT_TRY(build_cell_cubes(c, nx, ny, nz));
     RT_CUDA(cudaStreamSynchronize(c->stream));
     return RTGRFF_OK;
 }
@@ -770,9 +735,6 @@ int rtgrff_compose_cubes(rtgrff_ctx *c, int want_bvec)
     f.fxl = (float)(nx - 1); f.fyl = (float)(ny - 1); f.fzl = (float)(nz - 1);
     c->has_wcube = true; c->has_fcube = true; c->has_bvec = want_bvec != 0;
     c->stage_has_omega = true;
-    f.cm = 0;
-    RT_TRY(build_cell_cubes(c, nx, ny, nz));
-    RT_CUDA(cudaStreamSynchronize(c->stream));
     return RTGRFF_OK;
 }
 
@@ -849,8 +811,8 @@ static int prepare_sampler(rtgrff_ctx *c, SampleArgs &a, double r_sun_cm, double
     const size_t n = (size_t)a.n_rec * a.n_rays;
     RT_TRY(c->smp_ne.reserve(n * 4)); RT_TRY(c->smp_te.reserve(n * 4)); RT_TRY(c->smp_b.reserve(n * 4));
     RT_TRY(c->smp_ds.reserve(n * 4)); RT_TRY(c->smp_s.reserve(n * 4)); RT_TRY(c->smp_valid.reserve(n));
-    const float4 *unused_b;
-    sampler_cubes(c, false, a.fcube, unused_b, a.g);
+    a.fcube = c->fcube.as<float4>();
+    a.g = c->fgeomf;
     a.r_sun_cm = (float)r_sun_cm;   // numpy 2: float32 array * python float stays float32 (gpu_raytrace.py:482-484)
     a.fill_ne = (float)fill_ne; a.fill_te = (float)fill_te; a.fill_b = (float)fill_b;
     a.ne = c->smp_ne.as<float>(); a.te = c->smp_te.as<float>(); a.b = c->smp_b.as<float>();
@@ -1260,7 +1222,9 @@ int rtgrff_render_map(rtgrff_ctx *c, int64_t n_rays, const double *x_start, cons
     }
     MapArgs a;
     a.cube = rc;
-    sampler_cubes(c, use_bvec != 0, a.fcube, a.bcube, a.fg);
+    a.fcube = c->fcube.as<float4>();
+    a.bcube = c->has_bvec ? c->bcube.as<float4>() : nullptr;
+    a.fg = c->fgeomf;
     a.n_rays = n_rays;
     a.x_start = c->in0.as<double>(); a.y_start = c->in1.as<double>(); a.z_start = c->in2.as<double>();
     a.kvec = kvec ? c->in3.as<double>() : nullptr;
