@@ -1266,6 +1266,8 @@ int rtgrff_render_map(rtgrff_ctx *c, int64_t n_rays, const double *x_start, cons
     });
     // the per-frequency constants travel in the kernel parameters: kMaxFreqPerLaunch frequencies per launch
     const bool fork = kMaxFreqPerLaunch == 1 && n_freq > 1;
+    // launches in flight at once (RTGRFF_FORK_STREAMS, 1..8): the frequencies go round-robin over that many streams
+    static const int n_fork = [] { const char *e = getenv("RTGRFF_FORK_STREAMS"); int v = e ? atoi(e) : 8; return v < 1 ? 1 : (v > 8 ? 8 : v); }();
     cudaStream_t main_stream = c->stream;
     if (fork) {
         for (int q = 0; q < 8; ++q)
@@ -1283,7 +1285,7 @@ int rtgrff_render_map(rtgrff_ctx *c, int64_t n_rays, const double *x_start, cons
         rtgrff_ctx *c; cudaStream_t keep;
         ~StreamSwap() { c->stream = keep; }
     } swap{c, main_stream};
-    if (fork) c->stream = c->fstream[f0 % 8];
+    if (fork) c->stream = c->fstream[f0 % n_fork];
     switch (variant) {
         RT_MAP_CASE(0, false, 0, false, false) RT_MAP_CASE(1, false, 0, false, true)
         RT_MAP_CASE(2, false, 0, true, false) RT_MAP_CASE(3, false, 0, true, true)
