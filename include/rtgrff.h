@@ -285,6 +285,12 @@ int rtgrff_comm_destroy(rtgrff_ctx *ctx);
 int rtgrff_gather_image(rtgrff_ctx *ctx, const double *slab, int n_planes, int n_rows, int n_cols, int root,
                         double *image, int image_on_device);
 
+/* The root-side half of rtgrff_gather_image on its own, for hosts that move the slabs by other means (MPI, files):
+ * gathered = device float64 (world_size, n_planes, max_rows, n_cols), rank r's slab at index r; image = device
+ * float64 (n_planes, n_rows, n_cols) with every row at its place. */
+int rtgrff_place_rows(rtgrff_ctx *ctx, const double *gathered, int world_size, int n_planes, int n_rows, int n_cols,
+                      double *image);
+
 /*
  * Gaussian beam on the image plane: scipy.ndimage.gaussian_filter(map, sigma) as the workflow
  * applies it to its T_b maps (script/resample_with_ray_tracing.py:618-624; baseline beam of

@@ -39,7 +39,7 @@ EXPORTS = (
     "rtgrff_ctx_create_on_stream", "rtgrff_current_device", "rtgrff_get_mw_slice_device", "rtgrff_memcpy",
     "rtgrff_export_cubes", "rtgrff_shard_rows", "rtgrff_comm_unique_id", "rtgrff_comm_init_rank",
     "rtgrff_comm_destroy", "rtgrff_gather_image", "rtgrff_device_alloc", "rtgrff_device_free",
-    "rtgrff_ctx_set_pipeline", "rtgrff_ctx_set_grff64",
+    "rtgrff_ctx_set_pipeline", "rtgrff_ctx_set_grff64", "rtgrff_place_rows",
 )
 
 
@@ -79,6 +79,7 @@ def load():
     lib.rtgrff_comm_unique_id.argtypes = [ctypes.c_char_p]
     lib.rtgrff_comm_init_rank.argtypes = [c_void_p, c_int, c_int, ctypes.c_char_p]
     lib.rtgrff_comm_destroy.argtypes = [c_void_p]
+    lib.rtgrff_place_rows.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]
     lib.rtgrff_gather_image.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int]
     lib.rtgrff_ctx_destroy.argtypes = [c_void_p]
     lib.rtgrff_ctx_synchronize.argtypes = [c_void_p]

@@ -1378,6 +1378,20 @@ int rtgrff_comm_destroy(rtgrff_ctx *c)
     return RTGRFF_OK;
 }
 
+int rtgrff_place_rows(rtgrff_ctx *c, const double *gathered, int world_size, int n_planes, int n_rows, int n_cols,
+                      double *image)
+{
+    RT_USE(c);
+    if (!gathered || !image || world_size < 1 || n_planes < 1 || n_rows < 1 || n_cols < 1) return fail(RTGRFF_EINVAL, "bad arguments");
+    const int mr = max_rows_per_rank(n_rows, world_size), G = row_group_of(n_rows, world_size);
+    const size_t img_n = (size_t)n_planes * n_rows * n_cols;
+    const unsigned int blocks = (unsigned int)std::min<int64_t>(blocks_for((int64_t)img_n, 256), (int64_t)c->sm_count * 16);
+    place_rows_kernel<<<blocks, 256, 0, c->stream>>>(gathered, image, n_planes, n_rows, n_cols, mr, world_size, G);
+    RT_TRY(launched(c, "place_rows_kernel"));
+    RT_CUDA(cudaStreamSynchronize(c->stream));
+    return RTGRFF_OK;
+}
+
 int rtgrff_gather_image(rtgrff_ctx *c, const double *slab, int n_planes, int n_rows, int n_cols, int root, double *image,
                         int image_on_device)
 {

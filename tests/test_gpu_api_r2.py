@@ -306,3 +306,25 @@ def test_fp32_voxel_path_against_forced_fp64(session):
         assert rel.max() < 2e-5, rel.max()
     assert np.abs(out[0][1] - out[1][1]).max() < 2e-5 and np.abs(out[0][3] - out[1][3]).max() < 2e-5
     assert not np.array_equal(out[0][0], out[1][0])          # the two paths are different arithmetic
+
+
+@pytest.mark.parametrize("world,n_rows", [(2, 37), (3, 200), (8, 1000), (4, 64), (8, 2048)])
+def test_place_rows_with_ragged_shares(session, world, n_rows):
+    """The root-side reorder of the image gather for shares of unequal size (the benchmarks only ever have equal
+    ones): every rank's slab, padded to the largest share, in; the image with every row at its place out."""
+    import torch
+    from raytracinggrff_b200 import _lib, dist as rdist
+    n_planes, n_cols = 3, 11
+    rng = np.random.default_rng(world * 1000 + n_rows)
+    img = rng.random((n_planes, n_rows, n_cols))
+    mr = rdist.max_rows_per_rank(n_rows, world)
+    gathered = np.full((world, n_planes, mr, n_cols), np.nan)
+    for r in range(world):
+        rows, mr_c = rdist.c_shard_rows(n_rows, world, r)
+        assert mr_c == mr
+        gathered[r, :, :len(rows)] = img[:, rows]
+    g_d = torch.from_numpy(gathered).cuda()
+    out_d = torch.zeros((n_planes, n_rows, n_cols), dtype=torch.float64, device="cuda")
+    _lib.check(_lib.load().rtgrff_place_rows(session.ctx.handle, ctypes.c_void_p(g_d.data_ptr()), world, n_planes, n_rows,
+                                             n_cols, ctypes.c_void_p(out_d.data_ptr())))
+    assert np.array_equal(out_d.cpu().numpy(), img)
