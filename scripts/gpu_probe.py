@@ -101,8 +101,10 @@ def main():
         freqs = synthetic.log_frequencies(75e6, 8, np.log10(20.0) / 7)
         fps = [dict(freq_hz=float(f), **synthetic.frequency_scaled_params(float(f))) for f in freqs]
         ms = []
+        tile = tuple(int(t) for t in os.environ.get("RTGRFF_TILE", "4x8").split("x"))
         for _ in range(5):
-            tb, vi, st = ses.render_map(xs, ys, zs, fps, pixel_area_cm2=area, em_flag=4, use_bvec=True, image_shape=(512, 512))
+            tb, vi, st = ses.render_map(xs, ys, zs, fps, pixel_area_cm2=area, em_flag=4, use_bvec=True, image_shape=(512, 512),
+                                        tile=tile)
             ms.append(ses.ctx.last_kernel_ms)
         print("c4all ms:", " ".join(f"{m:.1f}" for m in ms), " best", min(ms), " checksum", float(tb.sum()), float(np.abs(vi).sum()))
     if which == "ncu_c4f":
