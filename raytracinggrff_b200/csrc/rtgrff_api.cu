@@ -1250,8 +1250,9 @@ int rtgrff_render_map(rtgrff_ctx *c, int64_t n_rays, const double *x_start, cons
         } else render_map_kernel<CS, ORD, BV, GR, MODE_F64><<<grid, block, 0, c->stream>>>(a);           \
         break;
     int mode = trace_variant() == 0 ? MODE_FAST32 : MODE_F64;
-    // the per-ray kernels use no shared memory: ask for the whole unified array as L1 (RTGRFF_CARVEOUT=-1 leaves the default)
-    static const int carve = getenv("RTGRFF_CARVEOUT") ? atoi(getenv("RTGRFF_CARVEOUT")) : 0;
+    // RTGRFF_CARVEOUT=<percent>: preferred shared-memory carve-out of the per-ray kernels (A/B switch; they use no
+    // shared memory and the default already gives them the whole unified array as L1: measured equal)
+    static const int carve = getenv("RTGRFF_CARVEOUT") ? atoi(getenv("RTGRFF_CARVEOUT")) : -1;
     for (int f = 0; f < n_freq; ++f)
         if (!(max_stage_offset_cells(freqs[f].dt, trace_cs ? perturb_ratio : 0.0, c->wgeom.idx, c->wgeom.idy,
                                      c->wgeom.idz) < kMaxStageOffsetCells))
