@@ -61,21 +61,6 @@ struct MapArgs {
     unsigned long long *active_steps;    // [0] active central steps, [1] steps with the pencil traced, [2] valid samples
 };
 
-// The float32 values a voxel is built from.  The transfer keeps the previous non-empty voxel in this
-// form — 6 registers live across the stepper instead of the 17 of a Voxel — and rebuilds the Voxel on
-// the rare occasions something happens between two voxels.
-struct VoxLite {
-    float dz, T, ne, B, cth, scale;
-};
-
-__device__ __forceinline__ Voxel voxel_of(const VoxLite &l, int flag, int smax)
-{
-    Voxel v = make_voxel_f(l.dz, l.T, l.ne, l.B, (double)l.cth, sqrt(fmax(0.0, 1.0 - (double)l.cth * (double)l.cth)),
-                           flag, smax);
-    v.scale = (double)l.scale;
-    return v;
-}
-
 // Transfer accumulated from the observer outwards (RTGRFF_ORDER_REVERSED): the records arrive
 // nearest-first, the radiation travels farthest-first.  I_obs = acc + M I_far with M a 2x2 matrix
 // in (L,R); folding one more (farther) operator I -> A I + b gives acc += M b, M = M A.
@@ -117,7 +102,11 @@ struct RecordTransfer {
         if (!voxel_nonempty_f(l.dz, l.T, l.ne, l.B, l.cth)) { have_prev = false; return; }
         if (NEED_BETWEEN) {
             if (have_prev && prev.B > 0.0f && l.B > 0.0f && between_needed_f(f, prev.cth, prev.B, l.cth, l.B, smax, !(flag & 1)))
-                st.apply(between_voxels(f, voxel_of(prev, flag, smax), voxel_of(l, flag, smax)));
+            {
+                Between b;
+                between_voxels_cold(f.nu, f.sn, prev, l, flag, smax, &b);
+                st.apply(b);
+            }
             prev = l;
             have_prev = true;
         }
@@ -135,7 +124,8 @@ struct OutwardTransferT : OutwardTransfer {
             if (have_prev && prev.B > 0.0f && l.B > 0.0f && between_needed_f(f, l.cth, l.B, prev.cth, prev.B, smax, !(flag & 1))) {
                 // radiation crosses v -> prev: between_voxels(v, prev) lists the events in that order,
                 // folding outwards meets them last-first
-                const Between b = between_voxels(f, voxel_of(l, flag, smax), voxel_of(prev, flag, smax));
+                Between b;
+                between_voxels_cold(f.nu, f.sn, l, prev, flag, smax, &b);
                 fold(b.after);
                 if (b.qt) fold_qt(b.Q);
                 fold(b.before);

@@ -394,6 +394,30 @@ __device__ __forceinline__ Between between_voxels(const FreqC &f, const Voxel &p
     return o;
 }
 
+// The float32 voxels of the per-ray kernels (fused map): what the transfer keeps of the previous non-empty voxel.
+struct VoxLite {
+    float dz, T, ne, B, cth, scale;
+};
+
+__device__ __forceinline__ Voxel voxel_of(const VoxLite &l, int flag, int smax)
+{
+    Voxel v = make_voxel_f(l.dz, l.T, l.ne, l.B, (double)l.cth, sqrt(fmax(0.0, 1.0 - (double)l.cth * (double)l.cth)),
+                           flag, smax);
+    v.scale = (double)l.scale;
+    return v;
+}
+
+// between_voxels for the per-ray kernels, OUT OF LINE: it runs on a fraction of a percent of the voxels (behind
+// between_needed_f), and inlined its acos / exp / lgamma chains sit in the instruction footprint and the register
+// allocation of the hot record loop.  The two per-frequency numbers it needs travel by value (a reference into
+// the kernel parameters would make the compiler copy the parameter block to local memory).
+__device__ __noinline__ void between_voxels_cold(double nu, double sn, VoxLite p, VoxLite k, int flag, int smax, Between *out)
+{
+    FreqC f;
+    f.nu = nu; f.sn = sn;
+    *out = between_voxels(f, voxel_of(p, flag, smax), voxel_of(k, flag, smax));
+}
+
 // Polarisation state for the three mode-coupling variants GRFF reports:
 // {L,R} weak (RL[1],RL[2]), strong (RL[3],RL[4]), exact (RL[5],RL[6]).
 template <int NVAR>
