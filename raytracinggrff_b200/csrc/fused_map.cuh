@@ -166,6 +166,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_MINB) render_map_kernel(const Map
             s.kx = 0.0 * kc0; s.ky = 0.0 * kc0; s.kz = -kc0;
         }
     }
+    if (MODE == MODE_FAST32 && has_ray) init_cell(C, s, cache);
     bool alive = has_ray;
     float s_step = CS ? 0.0f : 1.0f;
     double s_cum = 1.0;

@@ -291,6 +291,17 @@ __host__ __device__ __forceinline__ StepConst make_step_const(const RayCube &C, 
     return k;
 }
 
+// Before the first step of a ray: cache the cell of its start position (kept out of the step loop).  A start
+// outside the cube (or NaN) leaves the cache empty: step32 then reports the ray frozen at every step.
+__device__ __forceinline__ void init_cell(const RayCube &C, const State &s, Cell &cache)
+{
+    cache.off = -1;
+    if (!in_cube(C, s.rx, s.ry, s.rz)) return;
+    const double fx = (s.rx - C.x0) * C.idx, fy = (s.ry - C.y0) * C.idy, fz = (s.rz - C.z0) * C.idz;
+    cache.ci = min((int)fx, C.nx - 2); cache.cj = min((int)fy, C.ny - 2); cache.ck = min((int)fz, C.nz - 2);
+    load_cell(C, (cache.ci * C.ny + cache.cj) * C.nz + cache.ck, cache);
+}
+
 // One full step of the master state `s`: classic RK4 (build_rays.py:177-182) of the central ray
 // and, when `want_s` (warp-uniform), the same RK4 on the two pencil rays displaced by eps along
 // (e1, e2) _|_ t_hat with the cross-section ratio of this step (build_rays.py:209-239, with
@@ -302,12 +313,7 @@ __device__ __forceinline__ bool step32(const RayCube &C, const StepConst &K, Cel
                                        float &s_step)
 {
     const double fx = (s.rx - C.x0) * C.idx, fy = (s.ry - C.y0) * C.idy, fz = (s.rz - C.z0) * C.idz;
-    if (cache.off < 0) {
-        // first step of this ray: cache the cell of the start position
-        if (!in_cube(C, s.rx, s.ry, s.rz)) return false;
-        cache.ci = min((int)fx, C.nx - 2); cache.cj = min((int)fy, C.ny - 2); cache.ck = min((int)fz, C.nz - 2);
-        load_cell(C, (cache.ci * C.ny + cache.cj) * C.nz + cache.ck, cache);
-    }
+    if (cache.off < 0) return false;      // the ray started outside the cube (init_cell): frozen for ever
     // The cached cell is the cell of the last stage evaluated in the previous step, within m cells of
     // the previous master position (m = ceil of the largest stage offset, 1 for the usual dt); a step
     // moves the master by at most m cells and every stage of this step lies within m of the new

@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_MINB) trace_rays_kernel(const Tra
             s.kx = 0.0 * kc0; s.ky = 0.0 * kc0; s.kz = -kc0;
         }
     }
+    if (MODE == MODE_FAST32 && has_ray) init_cell(C, s, cache);
     bool alive = has_ray;
     float s_step = 0.0f;        // the ratio is a float32 quantity (MUFU-normalised pencil basis); the sampler casts it anyway
     double s_cum = 1.0;
