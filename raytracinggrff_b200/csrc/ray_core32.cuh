@@ -89,13 +89,24 @@ __device__ __forceinline__ void cell_poly(const float4 &c000, const float4 &c001
 #undef RT_HI
 }
 
+// The cell at `off` from the NODE cube (no polynomial cube: cubes too large to afford 128 B per cell): the 8 corners
+// are fetched and differenced here.  Out of line: with the polynomial cube present this never runs, and inlined at
+// every site a stage can leave the cached cell it put ~650 cold instructions into the middle of the hot loop.
+__device__ __noinline__ void load_cell_nodes(const float4 *__restrict__ nodes, int sx, int sy, int off, Cell *out)
+{
+    const float4 *p = nodes + off;
+    Cell c;
+    cell_poly(__ldg(p), __ldg(p + 1), __ldg(p + sy), __ldg(p + sy + 1), __ldg(p + sx), __ldg(p + sx + 1),
+              __ldg(p + sx + sy), __ldg(p + sx + sy + 1), c);
+    *out = c;
+}
+
 // Make the cell at element offset `off` the cached one.  With the cell-major polynomial cube
-// (build_poly_cube_kernel) that is 8 LDG.128 from one 128-byte line; without it (cube too large to
-// afford 128 B per cell) the 8 corners are fetched from the node cube and differenced here.
+// (build_poly_cube_kernel) that is 8 LDG.128 from one 128-byte line; without it: load_cell_nodes.
 __device__ __forceinline__ void load_cell(const RayCube &C, int off, Cell &c)
 {
-    c.off = off;
     if (C.pc) {
+        c.off = off;
         const float4 *p = C.pc + (size_t)off * 8;
         const float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2), q3 = __ldg(p + 3);
         const float4 q4 = __ldg(p + 4), q5 = __ldg(p + 5), q6 = __ldg(p + 6), q7 = __ldg(p + 7);
@@ -109,9 +120,9 @@ __device__ __forceinline__ void load_cell(const RayCube &C, int off, Cell &c)
 #undef RT_B
         return;
     }
-    const float4 *p = C.c + off;
-    cell_poly(__ldg(p), __ldg(p + 1), __ldg(p + C.sy), __ldg(p + C.sy + 1), __ldg(p + C.sx), __ldg(p + C.sx + 1),
-              __ldg(p + C.sx + C.sy), __ldg(p + C.sx + C.sy + 1), c);
+    const int ci = c.ci, cj = c.cj, ck = c.ck;       // the coordinates are the caller's business (set after the load)
+    load_cell_nodes(C.c, C.sx, C.sy, off, &c);
+    c.off = off; c.ci = ci; c.cj = cj; c.ck = ck;
 }
 
 // Node cube -> cell-major polynomial cube: cell (i,j,k), i < nx-1 etc., at [off*8, off*8+8) with the node

@@ -328,3 +328,29 @@ def test_place_rows_with_ragged_shares(session, world, n_rows):
     _lib.check(_lib.load().rtgrff_place_rows(session.ctx.handle, ctypes.c_void_p(g_d.data_ptr()), world, n_planes, n_rows,
                                              n_cols, ctypes.c_void_p(out_d.data_ptr())))
     assert np.array_equal(out_d.cpu().numpy(), img)
+
+
+def test_stepper_without_the_polynomial_cube_is_bit_identical(session, monkeypatch):
+    """Cubes too large for the 8x cell-major polynomial copy are stepped from the node cube, the cell's polynomial
+    differenced on the fly (load_cell_nodes): same arithmetic, same bits — paths and maps."""
+    c = synthetic.corona_cube(64, 3.0, active_region=True)
+    g3 = (c["x_grid"], c["y_grid"], c["z_grid"])
+    xs, ys, zs, kv = synthetic.ray_launch_geometry(12, 1.3, 3.0)
+    area = (2 * 1.3 / 12 * 6.957e10) ** 2
+    fps = [(90e6, 6e-3, 2500, 7), (600e6, 2.4e-3, 4000, 2)]
+    out = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("RTGRFF_POLY_CUBE", flag)
+        session.set_omega_cube(c["omega_pe"], *g3)
+        session.set_field_cubes(*g3, c["ne"], c["te"], c["b"], c["bx"], c["by"], c["bz"])
+        r, s, act = session.trace(90e6, xs, ys, zs, kv, 6e-3, 2500, 7, True, 2.0)
+        tb, vi, st = session.render_map(xs, ys, zs, fps, pixel_area_cm2=area, em_flag=4, use_bvec=True)
+        out[flag] = (r, s, act, tb, vi, st)
+    monkeypatch.delenv("RTGRFF_POLY_CUBE")
+    session.set_omega_cube(c["omega_pe"], *g3)            # leave the shared session with the default layout
+    for a, b in zip(out["1"], out["0"]):
+        if isinstance(a, np.ndarray):
+            assert np.array_equal(a, b, equal_nan=True)
+        else:
+            assert a == b
+    assert (out["1"][3] > 0).mean() > 0.3
