@@ -120,9 +120,12 @@ __device__ __forceinline__ void load_cell(const RayCube &C, int off, Cell &c)
 #undef RT_B
         return;
     }
-    const int ci = c.ci, cj = c.cj, ck = c.ck;       // the coordinates are the caller's business (set after the load)
-    load_cell_nodes(C.c, C.sx, C.sy, off, &c);
-    c.off = off; c.ci = ci; c.cj = cj; c.ck = ck;
+    // through a temporary: passing the address of the cache itself would pin all of it in local memory
+    Cell t;
+    load_cell_nodes(C.c, C.sx, C.sy, off, &t);
+    c.off = off;
+    c.l0 = t.l0; c.lz = t.lz; c.ly = t.ly; c.lyz = t.lyz; c.lx = t.lx; c.lxz = t.lxz; c.lxy = t.lxy; c.lxyz = t.lxyz;
+    c.h0 = t.h0; c.hz = t.hz; c.hy = t.hy; c.hyz = t.hyz; c.hx = t.hx; c.hxz = t.hxz; c.hxy = t.hxy; c.hxyz = t.hxyz;
 }
 
 // Node cube -> cell-major polynomial cube: cell (i,j,k), i < nx-1 etc., at [off*8, off*8+8) with the node
